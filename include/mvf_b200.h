@@ -1,0 +1,97 @@
+/*
+ * mvf_b200.h -- C ABI of libmvf_b200.so: hand-written sm_100a kernels for the MVFNet hot path.
+ *
+ * The reference (whwu95/MVFNet @ 0ddc7e2) has no native ABI: its hot path is Python calling stock
+ * torch.nn modules.  Each entry point below replaces the torch ops executed by the cited reference
+ * lines; the Python side of the boundary (mvfnet_b200/mvf.py, resnet.py) keeps the reference's
+ * module signatures and calls these through ctypes.
+ *
+ * Conventions
+ *   - extern "C", plain pointers + sizes, no C++/torch types.  All pointers are DEVICE pointers
+ *     unless stated otherwise; the caller owns every buffer; the library never frees or retains
+ *     them beyond the call (stream-ordered: buffers must stay alive until the stream reaches the
+ *     end of the enqueued work).
+ *   - Every call only enqueues work on `stream` (a cudaStream_t); no hidden device-wide sync.
+ *   - Return value 0 = success; otherwise an MVFB_ERR_* code, message via mvf_b200_last_error().
+ *   - dtype: MVFB_F32 or MVFB_BF16 (storage type of activations; arithmetic is always fp32).
+ *   - layout: MVFB_NCHW = (F, C, H, W) contiguous; MVFB_NHWC = (F, H, W, C) contiguous
+ *     (torch channels_last).  F = N*T frames, clip n owns frames [n*T, (n+1)*T).
+ */
+#ifndef MVF_B200_H_
+#define MVF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MVFB_VERSION 100
+
+enum { MVFB_OK = 0, MVFB_ERR_ARG = 1, MVFB_ERR_CUDA = 2, MVFB_ERR_UNSUPPORTED = 3, MVFB_ERR_WORKSPACE = 4 };
+enum { MVFB_F32 = 0, MVFB_BF16 = 1 };
+enum { MVFB_NCHW = 0, MVFB_NHWC = 1 };
+enum { MVFB_MODE_T = 0, MVFB_MODE_TH = 1, MVFB_MODE_THW = 2 };   /* MVF.py:112-129 `mode` */
+
+typedef void* mvfb_stream_t; /* cudaStream_t */
+
+int mvf_b200_version(void);
+/* Thread-local, NUL-terminated description of the last failure on this thread ("" if none). */
+const char* mvf_b200_last_error(void);
+/* Number of kernels launched by this library in this process so far (bench.py `gpu_launches`). */
+unsigned long long mvf_b200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * MVF module  --  replaces MVF.forward up to (not including) self.net: the view/transpose/split,
+ * three depthwise Conv3d, two adds, BatchNorm3d, HardSwish, cat and contiguous of
+ * codes/models/modules/MVF.py:109-137 (+ common/se_module.py:5-24).
+ *
+ *   z = sum_k wt[c,k] x[n,t+k-1,c,h,w] + sum_k wh[c,k] x[n,t,c,h+k-1,w] + sum_k ww[c,k] x[n,t,c,h,w+k-1]
+ *   u = gamma (z - mean)/sqrt(var+eps) + beta ;  y = u * clamp(u+3,0,6)/6      (use_hs)
+ * for channels c < Cs; zero padding; the T axis never crosses a clip.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int N, T, C, Cs, H, W;  /* x is (N*T, C, H, W); Cs = int(C*alpha) slab channels (MVF.py:59)      */
+  int dtype, layout;      /* MVFB_F32|MVFB_BF16, MVFB_NCHW|MVFB_NHWC                                */
+  int mode;               /* MVFB_MODE_*; share=True is expressed by passing wh == ww == wt          */
+  int use_hs;             /* 1: BatchNorm3d + HardSwish (MVF.py:131-134); 0: y = z                   */
+  int training;           /* 1: batch statistics + running-stat update; 0: running statistics        */
+  float eps, momentum;    /* BatchNorm3d defaults 1e-5, 0.1                                          */
+} mvfb_mvf_desc;
+
+/* Bytes of scratch `workspace` the forward / backward need for this descriptor. */
+size_t mvf_fwd_workspace_bytes(const mvfb_mvf_desc* d);
+size_t mvf_bwd_workspace_bytes(const mvfb_mvf_desc* d);
+
+/*
+ * Forward.  Writes ONLY the slab channels [0,Cs) of every pixel to `y`:
+ *   NCHW: y[f*y_stride + (c*H + h)*W + w]      (y_stride = C*H*W writes into a full tensor,
+ *                                               Cs*H*W into a compact (F,Cs,H,W) slab)
+ *   NHWC: y[((f*H + h)*W + w)*y_stride + c]    (y_stride = C or Cs)
+ * x is never modified (it is the residual identity, backbones/resnet.py:211).
+ * wt/wh/ww: fp32 (Cs,3) taps = shift_conv/h_conv/w_conv weights; wh/ww ignored per `mode`.
+ * gamma/beta/running_*: fp32 (Cs); save_mean/save_rstd: fp32 (Cs) outputs (training; may be NULL
+ * in eval).  training: running_mean/var are updated in place with momentum (unbiased variance).
+ */
+int mvf_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_stride, const float* wt, const float* wh,
+            const float* ww, const float* gamma, const float* beta, float* running_mean, float* running_var,
+            float* save_mean, float* save_rstd, void* workspace, size_t workspace_bytes, mvfb_stream_t stream);
+
+/*
+ * Backward.  g = dL/dy addressed like y (g_stride); dx receives dL/dx for slab channels only,
+ * addressed like y (dx_stride) -- the pass-through channels' gradient is the caller's g itself.
+ * Outputs dwt/dwh/dww (Cs,3) fp32, dgamma/dbeta (Cs) fp32 are OVERWRITTEN.  With share (wh==wt and/or
+ * ww==wt) the views' tap gradients are summed into dwt and dwh/dww may be NULL.
+ * training: save_mean/save_rstd from the forward; eval: running stats.
+ */
+int mvf_bwd(const mvfb_mvf_desc* d, const void* g, long long g_stride, const void* x, void* dx, long long dx_stride,
+            const float* wt, const float* wh, const float* ww, const float* gamma, const float* beta,
+            const float* running_mean, const float* running_var, const float* save_mean, const float* save_rstd,
+            float* dwt, float* dwh, float* dww, float* dgamma, float* dbeta, void* workspace,
+            size_t workspace_bytes, mvfb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MVF_B200_H_ */
