@@ -37,3 +37,14 @@ def load_cases(fname):
         c, f = k.split("/", 1)
         cases.setdefault(c, {})[f] = z[k]
     return cases
+
+
+@pytest.fixture(autouse=True)
+def _exact_fp32_library_math():
+    """fp32 parity tests compare against an fp64 reference: keep cuDNN / cuBLAS out of TF32."""
+    import torch
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old

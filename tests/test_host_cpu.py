@@ -1,0 +1,200 @@
+"""CPU-side tests: the C-ABI library loads and exports every symbol include/mvf_b200.h declares, the host
+mirror of the reference interface (registry / config / model structure / state_dict keys / error behaviour),
+and the N>1 data-parallel gradient path on gloo with world_size 2."""
+import ctypes
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import GOLDEN, ROOT
+
+REF_CFG = "/root/reference/configs/MVFNet/K400/mvf_kinetics400_2d_rgb_r50_dense.py"
+
+
+def test_library_exports_every_declared_symbol():
+    from mvfnet_b200 import _lib
+    hdr = open(os.path.join(ROOT, "include", "mvf_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    names = set(re.findall(r"\b([a-z_0-9]+)\s*\(", hdr)) - {"defined"}
+    names = {n for n in names if n.startswith(("mvf_", "mvfb_", "conv", "bn_", "sgd_", "gemm_"))}
+    assert {"mvf_fwd", "mvf_bwd", "mvf_b200_version", "mvf_b200_last_error"} <= names
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for n in sorted(names):
+        assert hasattr(lib, n), "libmvf_b200.so does not export %s" % n
+    assert _lib.lib().mvf_b200_version() == 100 or _lib.lib().mvf_b200_version() > 100
+
+
+def test_abi_argument_errors_without_gpu():
+    """Argument validation happens before any CUDA call, so it is testable on a CPU-only box."""
+    from mvfnet_b200 import _lib
+    L = _lib.lib()
+    d = _lib.MvfDesc(N=1, T=4, C=8, Cs=0, H=3, W=3, dtype=0, layout=0, mode=2, use_hs=1, training=0, eps=1e-5, momentum=0.1)
+    rc = L.mvf_fwd(ctypes.byref(d), None, None, 0, None, None, None, None, None, None, None, None, None, None, 0, None)
+    assert rc == 1 and b"Cs" in L.mvf_b200_last_error()
+    d.Cs = 4
+    d.dtype = 7
+    rc = L.mvf_fwd(ctypes.byref(d), None, None, 0, None, None, None, None, None, None, None, None, None, None, 0, None)
+    assert rc == 1 and b"dtype" in L.mvf_b200_last_error()
+    with pytest.raises(_lib.MvfB200Error):
+        _lib.check(rc, "mvf_fwd")
+
+
+def test_registry_contract():
+    from mvfnet_b200 import Registry, build_from_cfg, RECOGNIZERS, BACKBONES, HEADS
+    assert "Recognizer2D" in RECOGNIZERS.module_dict and "ResNet" in BACKBONES.module_dict and "TSNClsHead" in HEADS.module_dict
+    r = Registry("thing")
+
+    @r.register_module
+    class A:
+        def __init__(self, x, y=2):
+            self.x, self.y = x, y
+
+    with pytest.raises(KeyError):
+        r.register_module(A)
+    with pytest.raises(TypeError):
+        r.register_module(lambda: 0)
+    cfg = dict(type="A", x=1)
+    a = build_from_cfg(cfg, r, dict(y=5))
+    assert (a.x, a.y) == (1, 5) and cfg == dict(type="A", x=1)
+    assert build_from_cfg(dict(type=A, x=3), r).x == 3
+    with pytest.raises(KeyError):
+        build_from_cfg(dict(type="B"), r)
+    with pytest.raises(TypeError):
+        build_from_cfg(dict(type=3), r)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CFG), reason="reference configs not on this box")
+@pytest.mark.parametrize("name,depth", [("r50", 50), ("r101", 101)])
+def test_unmodified_reference_config_builds_same_structure(name, depth):
+    """configs/MVFNet/K400/*.py drop in: same state_dict keys / parameter count as the reference model."""
+    from mvfnet_b200 import Config, build_recognizer, MVF
+    cfg = Config.fromfile(REF_CFG.replace("r50", name))
+    assert cfg.model.module_cfg.alpha == 0.125 and cfg.data.videos_per_gpu == 12
+    cfg.model.backbone.pretrained = None
+    m = build_recognizer(cfg.model, train_cfg=cfg.train_cfg, test_cfg=cfg.test_cfg)
+    z = np.load(GOLDEN + "/structure.npz")
+    assert list(m.state_dict().keys()) == [str(k) for k in z["keys_" + name]]
+    assert sum(p.numel() for p in m.parameters()) == int(z["params_" + name])
+    n_mvf = sum(isinstance(x, MVF) for x in m.modules())
+    assert n_mvf == {50: 9, 101: 26}[depth]
+    assert "type" not in cfg.model.module_cfg          # popped like recognizer2d.py:52
+
+
+def test_mvf_module_attributes_and_bypass():
+    from mvfnet_b200 import MVF
+    net = torch.nn.Conv2d(16, 4, 1, bias=False)
+    m = MVF(net, n_segment=4, in_channels=16, alpha=0.125, share=False, mode="TH")
+    assert m.num_shift_channel == 2 and m.split_sizes == [2, 14] and m.net is net and m.n_segment == 4
+    assert hasattr(m, "h_conv") and not hasattr(m, "w_conv") and m.mode == "TH" and m.use_hs is True
+    assert tuple(m.shift_conv.weight.shape) == (2, 1, 3, 1, 1) and tuple(m.h_conv.weight.shape) == (2, 1, 1, 3, 1)
+    assert sorted(k for k in m.state_dict()) == sorted(
+        ["net.weight", "shift_conv.weight", "h_conv.weight", "bn.weight", "bn.bias", "bn.running_mean", "bn.running_var",
+         "bn.num_batches_tracked"])
+    ms = MVF(net, 4, 16, alpha=0.5, share=True, mode="THW")
+    assert not hasattr(ms, "h_conv") and not hasattr(ms, "w_conv")
+    # Cs == 0: straight to self.net (MVF.py:108) -- the only CPU-executable path
+    m0 = MVF(net, 4, 16, alpha=0.0)
+    x = torch.randn(8, 16, 3, 3)
+    assert torch.equal(m0(x), net(x))
+    with pytest.raises(RuntimeError):
+        m(x)                                            # no CPU fallback for the fused kernels
+    with pytest.raises(ValueError):
+        MVF(net, 4, 16, alpha=0.5, mode="HW")
+
+
+def test_resnet_train_mode_semantics():
+    from mvfnet_b200 import ResNet
+    from torch.nn.modules.batchnorm import _BatchNorm
+    r = ResNet(50, norm_eval=True, out_indices=(3,))
+    r.train()
+    assert all(not m.training for m in r.modules() if isinstance(m, _BatchNorm))
+    r = ResNet(50, norm_eval=False, frozen_stages=1, out_indices=(3,))
+    r.train()
+    assert not r.bn1.training and not r.conv1.weight.requires_grad
+    assert all(not p.requires_grad for p in r.layer1.parameters()) and all(p.requires_grad for p in r.layer2.parameters())
+    with pytest.raises(KeyError):
+        ResNet(18)
+
+
+def test_checkpoint_roundtrip_strips_module_prefix(tmp_path):
+    from mvfnet_b200 import Bottleneck
+    from mvfnet_b200.checkpoint import load_checkpoint, save_checkpoint
+    a, b = Bottleneck(16, 4), Bottleneck(16, 4)
+    f = str(tmp_path / "c.pth")
+    torch.save({"state_dict": {"module." + k: v for k, v in a.state_dict().items()}}, f)
+    load_checkpoint(b, f, map_location="cpu", strict=True)
+    assert all(torch.equal(a.state_dict()[k], b.state_dict()[k]) for k in a.state_dict())
+    save_checkpoint(a, f, meta=dict(epoch=3))
+    ck = torch.load(f)
+    assert set(ck) == {"meta", "state_dict"} and ck["meta"]["epoch"] == 3
+
+
+# ---------------------------------------------------------------- N>1 path on gloo
+def _dp_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    sys.path.insert(0, ROOT)
+    from mvfnet_b200.dist import DistOptimizerHook, FlatGrads, MMDistributedDataParallel, allreduce_grads, init_dist
+    init_dist("pytorch", backend="gloo")
+    torch.manual_seed(100 + rank)                      # different initial weights per rank ...
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    ddp = MMDistributedDataParallel(net)               # ... made identical by the construction-time broadcast
+    w0 = [p.detach().clone() for p in net.parameters()]
+    flat = FlatGrads(net.parameters())
+    opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9, nesterov=True)
+    g = torch.Generator().manual_seed(7)
+    x_all, y_all = torch.randn(8, 6, generator=g), torch.randn(8, 3, generator=g)
+    xs, ys = x_all[rank::world], y_all[rank::world]    # DistributedSampler-style stride by rank
+
+    class Runner:
+        pass
+
+    r = Runner()
+    r.model, r.optimizer, r.flat_grads = ddp, opt, flat
+    hook = DistOptimizerHook(grad_clip=dict(max_norm=40, norm_type=2))
+    for _ in range(2):
+        r.outputs = {"loss": torch.nn.functional.mse_loss(ddp(xs), ys)}
+        hook.after_train_iter(r)
+    # reference-style (non-flat) path must give the same averaged gradients
+    net.zero_grad(set_to_none=True)
+    torch.nn.functional.mse_loss(net(xs), ys).backward()
+    allreduce_grads(net.parameters())
+    out[rank] = dict(w0=w0, w=[p.detach().clone() for p in net.parameters()],
+                     g=[p.grad.clone() for p in net.parameters()], numel=flat.numel())
+    dist.destroy_process_group()
+
+
+def test_two_rank_gradient_allreduce_matches_single_process():
+    world = 2
+    port = 29500 + (os.getpid() % 2000)
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_dp_worker, args=(world, port, out), nprocs=world, join=True)
+    a, b = out[0], out[1]
+    for p, q in zip(a["w0"], b["w0"]):
+        assert torch.equal(p, q)                       # broadcast from rank 0
+    for p, q in zip(a["w"], b["w"]):
+        assert torch.allclose(p, q, atol=1e-7)         # replicas stay in lock step
+    # single-process equivalent: full batch of 8, mean loss == average of the two half-batch gradients
+    torch.manual_seed(100)
+    net = torch.nn.Sequential(torch.nn.Linear(6, 5), torch.nn.ReLU(), torch.nn.Linear(5, 3))
+    opt = torch.optim.SGD(net.parameters(), lr=0.1, momentum=0.9, nesterov=True)
+    g = torch.Generator().manual_seed(7)
+    x_all, y_all = torch.randn(8, 6, generator=g), torch.randn(8, 3, generator=g)
+    for _ in range(2):
+        opt.zero_grad()
+        torch.nn.functional.mse_loss(net(x_all), y_all).backward()
+        torch.nn.utils.clip_grad_norm_(net.parameters(), 40)
+        opt.step()
+    for p, q in zip(net.parameters(), a["w"]):
+        assert torch.allclose(p, q, atol=1e-6)
+    opt.zero_grad()
+    torch.nn.functional.mse_loss(net(x_all), y_all).backward()
+    for p, q in zip(net.parameters(), a["g"]):
+        assert torch.allclose(p.grad, q, atol=1e-6)
+    assert a["numel"] == sum(p.numel() for p in net.parameters())

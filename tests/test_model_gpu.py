@@ -1,0 +1,108 @@
+"""GPU parity of the Bottleneck (+MVF) block and the whole Recognizer2D against golden vectors produced by
+the unmodified reference (oracle/make_golden.py), fp32 storage, tolerance 1e-3 relative."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_cases, GOLDEN
+from oracle.mvfnet_ref import synth_state_dict
+
+pytestmark = pytest.mark.gpu
+
+BNECK = load_cases("bottleneck_cases.npz")
+
+
+def rel_err(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
+
+
+@pytest.mark.parametrize("name", sorted(BNECK))
+@pytest.mark.parametrize("channels_last", [False, True])
+def test_bottleneck_golden(name, channels_last):
+    from mvfnet_b200 import Bottleneck, MVF
+    import torch.nn as nn
+    c = BNECK[name]
+    f, t, inpl, planes, h, w, stride, ds, has_mvf, training = [int(v) for v in c["meta"]]
+    downsample = None
+    if ds:
+        downsample = nn.Sequential(nn.Conv2d(inpl, planes * 4, 1, stride, bias=False), nn.BatchNorm2d(planes * 4))
+    blk = Bottleneck(inpl, planes, stride, 1, downsample)
+    if has_mvf:
+        blk.conv1 = MVF(blk.conv1, t, inpl, float(c["alpha"]), True, False, "THW")
+    sd = {k[3:]: torch.as_tensor(v) for k, v in c.items() if k.startswith("sd.")}
+    blk.load_state_dict(sd)
+    blk = blk.float().cuda().train(bool(training))
+    x = torch.as_tensor(c["x"]).float().cuda()
+    gy = torch.as_tensor(c["gy"]).float().cuda()
+    if channels_last:
+        x = x.contiguous(memory_format=torch.channels_last)
+    x.requires_grad_(True)
+    y = blk(x)
+    y.backward(gy)
+    assert rel_err(y.detach().cpu().numpy(), c["out"]) < 1e-3
+    assert rel_err(x.grad.cpu().numpy(), c["dx"]) < 1e-3
+    for k, p in blk.named_parameters():
+        assert rel_err(p.grad.cpu().numpy(), c["g." + k]) < 1e-3, k
+    if training:
+        for k, v in blk.state_dict().items():
+            if "running" in k:
+                assert rel_err(v.cpu().numpy(), c["after." + k]) < 1e-3, k
+
+
+def model_cfg(depth, t, dropout):
+    return dict(
+        type="Recognizer2D",
+        backbone=dict(type="ResNet", pretrained=None, depth=depth, out_indices=(3,), norm_eval=False,
+                      partial_norm=False, norm_cfg=dict(type="BN", requires_grad=True)),
+        cls_head=dict(type="TSNClsHead", spatial_size=-1, spatial_type="avg", with_avg_pool=False,
+                      temporal_feature_size=1, spatial_feature_size=1, dropout_ratio=dropout,
+                      in_channels=2048, init_std=0.01, num_classes=400),
+        module_cfg=dict(type="MVF", n_segment=t, alpha=0.125, mvf_freq=(0, 0, 1, 1), mode="THW"))
+
+
+def test_whole_model_golden_fp32():
+    from mvfnet_b200 import build_recognizer
+    z = np.load(GOLDEN + "/model_r50.npz")
+    depth, t, b, px, seed = [int(v) for v in z["meta"]]
+    m = build_recognizer(model_cfg(depth, t, 0.0), None, dict(average_clips="prob"))
+    sd = synth_state_dict(seed, depth=depth, n_segment=t)
+    assert list(m.state_dict().keys()) == list(sd.keys())
+    m.load_state_dict(sd)
+    m = m.cuda()
+    img, label = torch.from_numpy(z["img"]).cuda(), torch.from_numpy(z["label"]).cuda()
+    m.eval()
+    with torch.no_grad():
+        prob = m(img, None, return_loss=False)
+    np.testing.assert_allclose(prob, z["eval_prob"], rtol=1e-3, atol=1e-6)
+    m.train()
+    loss = m(img, label)["loss_cls"]
+    loss.backward()
+    assert abs(loss.item() - float(z["train_loss"])) < 1e-3 * abs(float(z["train_loss"]))
+    norms = dict(zip([str(k) for k in z["grad_names"]], z["grad_norms"]))
+    for k, p in m.named_parameters():
+        assert abs(p.grad.double().norm().item() - norms[k]) <= 5e-3 * norms[k] + 1e-7, k
+    for k in z.files:
+        if k.startswith("grad."):
+            g = dict(m.named_parameters())[k[5:]].grad.cpu().numpy()
+            assert rel_err(g, z[k]) < 5e-3, k
+    rm = m.state_dict()["backbone.layer4.2.conv1.bn.running_mean"].cpu().numpy()
+    assert rel_err(rm, z["rm_after.layer4.2.conv1.bn"]) < 1e-3
+
+
+def test_whole_model_bf16_channels_last_runs():
+    """The bench configuration (bf16 autocast, channels_last): loss close to the fp32 golden loss."""
+    from mvfnet_b200 import build_recognizer
+    z = np.load(GOLDEN + "/model_r50.npz")
+    depth, t, b, px, seed = [int(v) for v in z["meta"]]
+    m = build_recognizer(model_cfg(depth, t, 0.0), None, dict(average_clips="prob"))
+    m.load_state_dict(synth_state_dict(seed, depth=depth, n_segment=t))
+    m = m.cuda().to(memory_format=torch.channels_last).train()
+    img, label = torch.from_numpy(z["img"]).cuda(), torch.from_numpy(z["label"]).cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = m(img, label)["loss_cls"]
+    loss.backward()
+    assert abs(loss.item() - float(z["train_loss"])) < 3e-2 * abs(float(z["train_loss"]))
+    for k, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), k
