@@ -165,6 +165,7 @@ def run_ours(args):
     from mvfnet_b200 import build_recognizer, _lib
     from mvfnet_b200 import mvf as mvf_mod
     from mvfnet_b200.dist import FlatGrads, init_dist
+    from mvfnet_b200.utils import to_channels_last
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -178,7 +179,7 @@ def run_ours(args):
     torch.backends.cudnn.benchmark = True                         # cfg: cudnn_benchmark = True (r50_dense.py:180)
     B = args.batch
     torch.manual_seed(0)
-    model = build_recognizer(model_cfg(), None, None).to(dev).to(memory_format=torch.channels_last).train()
+    model = to_channels_last(build_recognizer(model_cfg(), None, None).to(dev)).train()
     if world > 1:                                                  # MMDistributedDataParallel: broadcast once
         for t in model.state_dict().values():
             dist.broadcast(t, 0)

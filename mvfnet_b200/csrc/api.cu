@@ -114,13 +114,17 @@ unsigned long long mvf_b200_launch_count(void) { return g_launches.load(std::mem
 
 size_t mvf_fwd_workspace_bytes(const mvfb_mvf_desc* d) {
   if (!d) return 0;
-  return 16 * sizeof(double) * (size_t)d->Cs + 256;
+  size_t generic = 16 * sizeof(double) * (size_t)d->Cs + 256;
+  size_t fast = mvf_fast_supported(d) ? mvf_fast_ws(d) : 0;
+  return generic > fast ? generic : fast;
 }
 
 size_t mvf_bwd_workspace_bytes(const mvfb_mvf_desc* d) {
   if (!d) return 0;
-  if (mvf_fast_supported(d)) return mvf_fast_bwd_ws(d);
-  return mvf_generic_bwd_ws(d);
+  // both paths are sized: the fast path can still decline at run time (pointer / stride alignment)
+  size_t generic = mvf_generic_bwd_ws(d);
+  size_t fast = mvf_fast_bwd_supported(d) ? 2 * sizeof(float) * (((size_t)d->Cs + 63) / 64 * 64) + mvf_fast_ws(d) : 0;
+  return generic > fast ? generic : fast;
 }
 
 int mvf_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_stride, const float* wt, const float* wh,
@@ -139,9 +143,11 @@ int mvf_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_stride, 
   MVFB_CHECK(workspace_bytes >= mvf_fwd_workspace_bytes(d) && workspace, MVFB_ERR_WORKSPACE,
              "workspace too small: %zu < %zu", workspace_bytes, mvf_fwd_workspace_bytes(d));
   cudaStream_t st = (cudaStream_t)stream;
-  if (mvf_fast_supported(d))
-    return mvf_fast_fwd(d, x, y, y_stride, wt, wh, ww, gamma, beta, running_mean, running_var, save_mean, save_rstd,
-                        workspace, st);
+  if (mvf_fast_supported(d)) {
+    rc = mvf_fast_fwd(d, x, y, y_stride, wt, wh, ww, gamma, beta, running_mean, running_var, save_mean, save_rstd,
+                      workspace, st);
+    if (rc != MVFB_ERR_UNSUPPORTED) return rc;   // unaligned pointers / strides: take the layout-generic kernels
+  }
   return mvf_generic_fwd(d, x, y, y_stride, wt, wh, ww, gamma, beta, running_mean, running_var, save_mean, save_rstd,
                          workspace, st);
 }
@@ -186,9 +192,11 @@ int mvf_bwd(const mvfb_mvf_desc* d, const void* g, long long g_stride, const voi
     }
   }
   ws += 2 * sizeof(float) * (((size_t)d->Cs + 63) / 64 * 64);
-  if (mvf_fast_supported(d))
-    return mvf_fast_bwd(d, g, g_stride, x, dx, dx_stride, wt, wh, ww, gamma, beta, mean, rstd, dwt, dwh, dww, dgamma,
-                        dbeta, ws, st);
+  if (mvf_fast_bwd_supported(d)) {
+    rc = mvf_fast_bwd(d, g, g_stride, x, dx, dx_stride, wt, wh, ww, gamma, beta, mean, rstd, dwt, dwh, dww, dgamma,
+                      dbeta, ws, st);
+    if (rc != MVFB_ERR_UNSUPPORTED) return rc;
+  }
   return mvf_generic_bwd(d, g, g_stride, x, dx, dx_stride, wt, wh, ww, gamma, beta, mean, rstd, dwt, dwh, dww, dgamma,
                          dbeta, ws, st);
 }

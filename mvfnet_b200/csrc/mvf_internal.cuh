@@ -23,10 +23,11 @@ int mvf_eval_stats(const float* rm, const float* rv, float eps, int Cs, float* m
 
 // ---- mvf_fast.cu : bf16 NHWC, TMA-staged (T,H,W) tiles in shared memory
 bool mvf_fast_supported(const mvfb_mvf_desc* d);
+bool mvf_fast_bwd_supported(const mvfb_mvf_desc* d);
+size_t mvf_fast_ws(const mvfb_mvf_desc* d);
 int mvf_fast_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_stride, const float* wt,
                 const float* wh, const float* ww, const float* gamma, const float* beta, float* rm, float* rv,
                 float* save_mean, float* save_rstd, void* ws, cudaStream_t st);
-size_t mvf_fast_bwd_ws(const mvfb_mvf_desc* d);
 int mvf_fast_bwd(const mvfb_mvf_desc* d, const void* g, long long g_stride, const void* x, void* dx,
                 long long dx_stride, const float* wt, const float* wh, const float* ww, const float* gamma,
                 const float* beta, const float* mean, const float* rstd, float* dwt, float* dwh, float* dww,

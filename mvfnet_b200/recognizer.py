@@ -1,6 +1,7 @@
 """Recognizer2D: (B, T, 3, H, W) clips -> backbone on (B*T, 3, H, W) frames -> head -> loss / scores.
 Mirrors codes/models/recognizers/base.py:11-82 and recognizer2d.py:8-179 for the RGB + ResNet + MVF
 configuration (configs/MVFNet/K400/*.py); the other module / backbone branches raise."""
+import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
@@ -26,6 +27,9 @@ class BaseRecognizer(nn.Module):
             self.cls_head.init_weights()
 
     def extract_feat(self, img_group):
+        if img_group.is_cuda and img_group.dim() == 4:
+            # the kernels' native activation layout is NHWC (torch channels_last); logical shape unchanged
+            img_group = img_group.contiguous(memory_format=torch.channels_last)
         return self.backbone(img_group)
 
     def average_clip(self, cls_score):

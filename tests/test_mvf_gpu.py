@@ -21,6 +21,19 @@ def rel_err(a, b):
     return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-12))
 
 
+def rel_err_kinks(a, b, max_outliers=8):
+    """rel_err for dL/dx through hard-swish: its derivative jumps by |u|/6 at u = +-3, so a handful of elements
+    whose u lies within rounding distance of a kink legitimately take the other branch in fp32 / bf16 than in
+    the fp64 oracle.  Ignore at most `max_outliers` such elements (out of >= 1e5)."""
+    a = np.asarray(a, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.float64).ravel()
+    err = np.abs(a - b)
+    k = min(max_outliers, max(err.size // 20000, 0))
+    if k:
+        err = np.partition(err, err.size - k - 1)[:err.size - k]
+    return float(err.max() / max(np.abs(b).max(), 1e-12))
+
+
 def build_mvf(cs_in, t, alpha, mode, share, use_hs, params, rm, rv, training, dev="cuda"):
     from mvfnet_b200 import MVF
     m = MVF(torch.nn.Identity(), t, cs_in, alpha=alpha, use_hs=use_hs, share=share, mode=mode)
@@ -144,7 +157,7 @@ def test_mvf_vs_oracle_model_shapes(C, H, Cs, T, training, dtype):
     rb = O.mvf_backward(gs, xs, T, Cs, training=training, **kw)
     assert rel_err(y.detach().double().cpu().numpy(), rf["out"]) < tol
     assert torch.equal(y.detach()[:, Cs:], xd.detach()[:, Cs:])
-    assert rel_err(xd.grad.double().cpu().numpy(), rb["dx"]) < 2 * tol
+    assert rel_err_kinks(xd.grad.double().cpu().numpy(), rb["dx"]) < 2 * tol
     gt = 2 * tol if dtype == "f32" else 4 * tol
     assert rel_err(m.shift_conv.weight.grad.double().cpu().numpy().reshape(Cs, 3), rb["dwt"]) < gt
     assert rel_err(m.h_conv.weight.grad.double().cpu().numpy().reshape(Cs, 3), rb["dwh"]) < gt
@@ -158,35 +171,50 @@ def test_mvf_vs_oracle_model_shapes(C, H, Cs, T, training, dtype):
 
 @pytest.mark.parametrize("mode,share,use_hs", [("T", False, True), ("TH", False, True), ("THW", True, True),
                                                 ("TH", True, False), ("THW", False, False)])
-def test_mvf_variants_vs_oracle(mode, share, use_hs):
+@pytest.mark.parametrize("dtype,training", [("f32", True), ("bf16", True), ("bf16", False)])
+def test_mvf_variants_vs_oracle(mode, share, use_hs, dtype, training):
     from mvfnet_b200 import MVF
     N, T, C, H, W, Cs = 3, 8, 64, 14, 14, 16
+    tdt = torch.float32 if dtype == "f32" else torch.bfloat16
+    tol = 1e-3 if dtype == "f32" else 1e-2
     g = torch.Generator().manual_seed(7)
     m = MVF(torch.nn.Identity(), T, C, alpha=0.25, use_hs=use_hs, share=share, mode=mode)
     with torch.no_grad():
         for p in m.parameters():
             p.copy_(torch.randn(p.shape, generator=g) * 0.5 + (1.0 if p.dim() == 1 else 0.0))
-    m = m.cuda().train(True)
-    x = torch.randn((N * T, C, H, W), generator=g)
-    gy = torch.randn((N * T, C, H, W), generator=g)
-    xd = x.cuda().requires_grad_(True)
+    rm0 = torch.randn(Cs, generator=g)
+    rv0 = 0.5 + torch.rand(Cs, generator=g)
+    with torch.no_grad():
+        m.bn.running_mean.copy_(rm0)
+        m.bn.running_var.copy_(rv0)
+    m = m.cuda().train(training)
+    x = torch.randn((N * T, C, H, W), generator=g).to(tdt)
+    gy = torch.randn((N * T, C, H, W), generator=g).to(tdt)
+    xd = x.cuda()
+    gd = gy.cuda()
+    if dtype == "bf16":
+        xd = xd.contiguous(memory_format=torch.channels_last)
+        gd = gd.contiguous(memory_format=torch.channels_last)
+    xd.requires_grad_(True)
     y = m(xd)
-    y.backward(gy.cuda())
+    y.backward(gd)
     tap = lambda name: getattr(m, name).weight.detach().double().cpu().numpy().reshape(Cs, 3) if hasattr(m, name) else None
     kw = dict(wt=tap("shift_conv"), wh=tap("h_conv"), ww=tap("w_conv"), gamma=m.bn.weight.detach().double().cpu().numpy(),
-              beta=m.bn.bias.detach().double().cpu().numpy(), running_mean=np.zeros(Cs), running_var=np.ones(Cs),
+              beta=m.bn.bias.detach().double().cpu().numpy(), running_mean=rm0.double().numpy(), running_var=rv0.double().numpy(),
               mode=mode, share=share, use_hs=use_hs)
-    rf = O.mvf_forward(x.double().numpy(), T, Cs, training=True, **kw)
-    rb = O.mvf_backward(gy.double().numpy(), x.double().numpy(), T, Cs, training=True, **kw)
-    assert rel_err(y.detach().cpu().numpy(), rf["out"]) < 1e-3
-    assert rel_err(xd.grad.cpu().numpy(), rb["dx"]) < 2e-3
-    assert rel_err(m.shift_conv.weight.grad.cpu().numpy().reshape(Cs, 3), rb["dwt"]) < 2e-3
+    rf = O.mvf_forward(x.double().numpy(), T, Cs, training=training, **kw)
+    rb = O.mvf_backward(gy.double().numpy(), x.double().numpy(), T, Cs, training=training, **kw)
+    assert rel_err(y.detach().double().cpu().numpy(), rf["out"]) < tol
+    assert rel_err_kinks(xd.grad.double().cpu().numpy(), rb["dx"]) < 2 * tol
+    gt = 2 * tol if dtype == "f32" else 4 * tol
+    assert rel_err(m.shift_conv.weight.grad.double().cpu().numpy().reshape(Cs, 3), rb["dwt"]) < gt
     if rb["dwh"] is not None:
-        assert rel_err(m.h_conv.weight.grad.cpu().numpy().reshape(Cs, 3), rb["dwh"]) < 2e-3
+        assert rel_err(m.h_conv.weight.grad.double().cpu().numpy().reshape(Cs, 3), rb["dwh"]) < gt
     if rb["dww"] is not None:
-        assert rel_err(m.w_conv.weight.grad.cpu().numpy().reshape(Cs, 3), rb["dww"]) < 2e-3
+        assert rel_err(m.w_conv.weight.grad.double().cpu().numpy().reshape(Cs, 3), rb["dww"]) < gt
     if use_hs:
-        assert rel_err(m.bn.weight.grad.cpu().numpy(), rb["dgamma"]) < 2e-3
+        assert rel_err(m.bn.weight.grad.double().cpu().numpy(), rb["dgamma"]) < gt
+        assert rel_err(m.bn.bias.grad.double().cpu().numpy(), rb["dbeta"]) < gt
     else:
         assert m.bn.weight.grad is None
 
