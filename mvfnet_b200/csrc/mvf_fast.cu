@@ -16,6 +16,7 @@
 // a 3-slot fp32 ring (zero halo), accumulates the 7 tap-gradient sums against the staged x neighbours and
 // emits dx(t-1) = transposed stencil of dz(t-2..t).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "mvf_internal.cuh"
@@ -344,6 +345,225 @@ mvf_fast_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const FwdArgs a) {
     for (int i = tid; i < 2 * g.Cg; i += kThreads) {
       const int ch = i >> 1, kind = i & 1;
       a.partials[((size_t)n * g.Cs + c0) * 2 + i] = s_out[(ch / V) * (2 * V) + kind * V + (ch % V)];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------ forward, resident clip
+// Second-generation forward kernel for T in {4, 8, 16} when the whole clip volume of the channel group fits
+// in shared memory.  The first kernel above is bound by instruction issue (40 lane-instructions per element,
+// ncu r1d), not by HBM, so this one minimises instructions per element:
+//   * every thread owns fixed (pixel, 8-channel vector) items and walks t = 0..T-1 with the unpacked centre
+//     values of frames t-1, t, t+1 rolling through registers (fully unrolled: no moves), so only 5 instead of
+//     7 shared-memory vectors are loaded and unpacked per output vector;
+//   * all arithmetic is packed fp32x2 (FFMA2 on sm_100): 28 instead of 56 FMAs per vector;
+//   * no per-frame barriers: the T frame loads are all in flight from the first instruction of the CTA and
+//     are waited for once; the temporal zero padding lives in registers, so no zero slot is needed.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b) { return __fadd2_rn(a, b); }
+
+struct F8 {
+  float2 p[4];
+};
+__device__ __forceinline__ F8 lds_unpack8(const uint8_t* ptr) {
+  const uint4 v = *reinterpret_cast<const uint4*>(ptr);
+  F8 r;
+  r.p[0] = make_float2(bf16_lo(v.x), bf16_hi(v.x));
+  r.p[1] = make_float2(bf16_lo(v.y), bf16_hi(v.y));
+  r.p[2] = make_float2(bf16_lo(v.z), bf16_hi(v.z));
+  r.p[3] = make_float2(bf16_lo(v.w), bf16_hi(v.w));
+  return r;
+}
+__device__ __forceinline__ F8 zero8() {
+  F8 r;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) r.p[j] = make_float2(0.f, 0.f);
+  return r;
+}
+struct Coef8 {
+  F8 c, t0, t2, h0, h2, w0, w2;
+  __device__ __forceinline__ void load(const float* wt, const float* wh, const float* ww, int ch0) {
+    float a[7][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c3 = (ch0 + j) * 3;
+      a[1][j] = wt[c3]; a[0][j] = wt[c3 + 1]; a[2][j] = wt[c3 + 2];
+      a[3][j] = a[4][j] = a[5][j] = a[6][j] = 0.f;
+      if (wh) { a[3][j] = wh[c3]; a[0][j] += wh[c3 + 1]; a[4][j] = wh[c3 + 2]; }
+      if (ww) { a[5][j] = ww[c3]; a[0][j] += ww[c3 + 1]; a[6][j] = ww[c3 + 2]; }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      c.p[j] = make_float2(a[0][2 * j], a[0][2 * j + 1]);
+      t0.p[j] = make_float2(a[1][2 * j], a[1][2 * j + 1]);
+      t2.p[j] = make_float2(a[2][2 * j], a[2][2 * j + 1]);
+      h0.p[j] = make_float2(a[3][2 * j], a[3][2 * j + 1]);
+      h2.p[j] = make_float2(a[4][2 * j], a[4][2 * j + 1]);
+      w0.p[j] = make_float2(a[5][2 * j], a[5][2 * j + 1]);
+      w2.p[j] = make_float2(a[6][2 * j], a[6][2 * j + 1]);
+    }
+  }
+};
+
+template <int PASS, int T>
+__global__ void __launch_bounds__(kThreads, 2)
+mvf_fwd_resident_kernel(const __grid_constant__ CUtensorMap tmx, const FwdArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const Geo& g = a.g;
+  const int tid = threadIdx.x;
+  const int G = g.Cg / 8;
+  const int ngroups = g.Cs / g.Cg;
+  const int n = blockIdx.x / ngroups, cg = blockIdx.x - n * ngroups;
+  const int c0 = cg * g.Cg;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem);
+  uint8_t* slots = smem + 256;
+  uint8_t* rest = slots + (size_t)T * g.slot_x;
+  float* s_scale = reinterpret_cast<float*>(rest);            // [Cg]
+  float* s_shift = s_scale + g.Cg;                            // [Cg]
+  float* s_red = s_shift + g.Cg;                              // [kWarps][G][16] floats / doubles for partials
+  float* s_out = s_red + kWarps * G * 16;                     // [G][16]
+
+  if (tid == 0) {
+    tma_prefetch_desc(&tmx);
+#pragma unroll
+    for (int t = 0; t < T; ++t) mbar_init(&bars[t], 1);
+    fence_barrier_init();
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      mbar_arrive_expect_tx(&bars[t], (uint32_t)(g.Hp * g.Wp * g.Cg * 2));
+      tma_load_4d(slots + (size_t)t * g.slot_x, &tmx, &bars[t], c0, -1, -1, n * T + t);
+    }
+  }
+  __syncthreads();                                            // barrier inits visible before anyone waits
+
+  if (PASS == PASS_TRAIN) {
+    double* dpart = reinterpret_cast<double*>(s_red);
+    double* dsum = dpart + kThreads;
+    reduce_partials(a.partials, g.N, g.Cs, c0, g.Cg, dpart, dsum);
+    if (tid < g.Cg) {
+      const int c = c0 + tid;
+      const double m = (double)g.N * T * g.H * g.W;
+      const double mu = dsum[tid * 2] / m;
+      double var = dsum[tid * 2 + 1] / m - mu * mu;
+      if (var < 0) var = 0;
+      const float mean = (float)mu, rstd = (float)(1.0 / sqrt(var + (double)a.eps));
+      const float sc = a.gamma[c] * rstd;
+      s_scale[tid] = sc;
+      s_shift[tid] = a.beta[c] - mean * sc;
+      if (n == 0) {
+        a.save_mean[c] = mean;
+        a.save_rstd[c] = rstd;
+        if (a.running_mean) {
+          const double unb = m > 1 ? var * m / (m - 1) : var;
+          a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * mean;
+          a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * (float)unb;
+        }
+      }
+    }
+    __syncthreads();
+  } else if (PASS == PASS_APPLY) {
+    if (tid < g.Cg) {
+      const int c = c0 + tid;
+      float sc = 1.f, sh = 0.f;
+      if (a.use_hs) {
+        const float mean = a.running_mean[c], rstd = 1.f / sqrtf(a.running_var[c] + a.eps);
+        sc = a.gamma[c] * rstd;
+        sh = a.beta[c] - mean * sc;
+        if (n == 0 && a.save_mean) { a.save_mean[c] = mean; a.save_rstd[c] = rstd; }
+      }
+      s_scale[tid] = sc;
+      s_shift[tid] = sh;
+    }
+    __syncthreads();
+  }
+
+  const int vec = tid % G, ch0 = c0 + vec * 8;
+  Coef8 k;
+  k.load(a.wt, a.wh, a.ww, ch0);
+  F8 scale, shift;
+  if (PASS != PASS_STATS) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      scale.p[j] = make_float2(s_scale[vec * 8 + 2 * j], s_scale[vec * 8 + 2 * j + 1]);
+      shift.p[j] = make_float2(s_shift[vec * 8 + 2 * j], s_shift[vec * 8 + 2 * j + 1]);
+    }
+  }
+  F8 sum = zero8(), sq = zero8();
+  Walk wk;
+  wk.init(tid, G, g.H, g.W);
+  const int pixb = g.Cg * 2, rowb = g.Wp * pixb;
+  const size_t frame_elems = (size_t)g.H * g.W * a.y_pix;
+  const bool hs = a.use_hs != 0;
+
+#pragma unroll 1
+  for (int t = 0; t < T; ++t) mbar_wait(&bars[t], 0);
+
+  int h = wk.h0, w = wk.w0;
+#pragma unroll 1
+  for (int i = tid; i < wk.items; i += kThreads) {
+    const uint8_t* p0 = slots + ((h + 1) * g.Wp + (w + 1)) * pixb + vec * 16;
+    __nv_bfloat16* yp = a.y + ((size_t)n * T * g.H * g.W + (size_t)(h * g.W + w)) * a.y_pix + ch0;
+    F8 xm = zero8(), xc = lds_unpack8(p0), xp;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+      const uint8_t* pt = p0 + (size_t)t * g.slot_x;
+      xp = (t + 1 < T) ? lds_unpack8(pt + g.slot_x) : zero8();
+      F8 z;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) z.p[j] = ffma2(k.t2.p[j], xp.p[j], ffma2(k.t0.p[j], xm.p[j], fmul2(k.c.p[j], xc.p[j])));
+      F8 f = lds_unpack8(pt - rowb);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) z.p[j] = ffma2(k.h0.p[j], f.p[j], z.p[j]);
+      f = lds_unpack8(pt + rowb);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) z.p[j] = ffma2(k.h2.p[j], f.p[j], z.p[j]);
+      f = lds_unpack8(pt - pixb);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) z.p[j] = ffma2(k.w0.p[j], f.p[j], z.p[j]);
+      f = lds_unpack8(pt + pixb);
+#pragma unroll
+      for (int j = 0; j < 4; ++j) z.p[j] = ffma2(k.w2.p[j], f.p[j], z.p[j]);
+      if (PASS == PASS_STATS) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          sum.p[j] = fadd2(sum.p[j], z.p[j]);
+          sq.p[j] = ffma2(z.p[j], z.p[j], sq.p[j]);
+        }
+      } else {
+        if (hs) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float2 u = ffma2(z.p[j], scale.p[j], shift.p[j]);
+            float2 s;
+            s.x = __saturatef(fmaf(u.x, 1.f / 6.f, 0.5f));
+            s.y = __saturatef(fmaf(u.y, 1.f / 6.f, 0.5f));
+            z.p[j] = fmul2(u, s);
+          }
+        }
+        uint4 o;
+        o.x = pack_bf16(z.p[0].x, z.p[0].y); o.y = pack_bf16(z.p[1].x, z.p[1].y);
+        o.z = pack_bf16(z.p[2].x, z.p[2].y); o.w = pack_bf16(z.p[3].x, z.p[3].y);
+        *reinterpret_cast<uint4*>(yp + (size_t)t * frame_elems) = o;
+      }
+      xm = xc;
+      xc = xp;
+    }
+    w += wk.dw; h += wk.dh;
+    if (w >= g.W) { w -= g.W; h += 1; }
+  }
+
+  if (PASS == PASS_STATS) {
+    float acc[16];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      acc[2 * j] = sum.p[j].x; acc[2 * j + 1] = sum.p[j].y;
+      acc[8 + 2 * j] = sq.p[j].x; acc[8 + 2 * j + 1] = sq.p[j].y;
+    }
+    cta_reduce_by_vector<16>(acc, G, s_red, s_out);
+    for (int i = tid; i < 2 * g.Cg; i += kThreads) {
+      const int ch = i >> 1, kind = i & 1;
+      a.partials[((size_t)n * g.Cs + c0) * 2 + i] = s_out[(ch / 8) * 16 + kind * 8 + (ch % 8)];
     }
   }
 }
@@ -747,9 +967,12 @@ int set_smem(K kernel, size_t bytes) {
 
 }  // namespace
 
+static bool choose_resident(const mvfb_mvf_desc* d, Geo& out, size_t& smem);
+
 bool mvf_fast_supported(const mvfb_mvf_desc* d) {
   Geo g;
-  return choose_geo(d, false, g);
+  size_t smem;
+  return choose_resident(d, g, smem) || choose_geo(d, false, g);
 }
 
 bool mvf_fast_bwd_supported(const mvfb_mvf_desc* d) {
@@ -759,11 +982,68 @@ bool mvf_fast_bwd_supported(const mvfb_mvf_desc* d) {
 
 size_t mvf_fast_ws(const mvfb_mvf_desc* d) { return (size_t)d->N * d->Cs * 2 * sizeof(float) + 256; }
 
+// resident-clip geometry: widest channel group whose whole (T, H+2, W+2) volume leaves room for two CTAs per SM
+// and still yields >= 2 CTAs per SM of work (or the narrowest that fits)
+static bool choose_resident(const mvfb_mvf_desc* d, Geo& out, size_t& smem) {
+  if (d->dtype != MVFB_BF16 || d->layout != MVFB_NHWC) return false;
+  if (d->T != 4 && d->T != 8 && d->T != 16) return false;
+  if (d->Cs % 8 != 0 || d->C % 8 != 0 || d->H + 2 > 256 || d->W + 2 > 256) return false;
+  const int want = 2 * num_sms();
+  const int cands[4] = {64, 32, 16, 8};
+  bool found = false;
+  static const int forced = getenv("MVFB_CG") ? atoi(getenv("MVFB_CG")) : 0;   // tuning experiments only
+  for (int i = 0; i < 4; ++i) {
+    const int Cg = cands[i];
+    if (d->Cs % Cg) continue;
+    if (forced && Cg != forced) continue;
+    if (Cg == 8 && found) break;
+    Geo g;
+    fill_geo(g, d, Cg, d->T);
+    const int G = Cg / 8;
+    const size_t need = 256 + (size_t)d->T * g.slot_x + 2 * Cg * 4 + (size_t)kWarps * G * 16 * 4 + G * 16 * 4 + 3 * kThreads * 8;
+    if (need > (size_t)kSmemLimit) continue;
+    if (need > 112 * 1024 && Cg > 16 && !forced) continue;
+    out = g;
+    smem = need;
+    found = true;
+    if ((long long)d->N * (d->Cs / Cg) >= want) break;
+  }
+  return found;
+}
+
+template <int T>
+static int launch_resident(const mvfb_mvf_desc* d, const CUtensorMap& tmx, const FwdArgs& a, size_t smem,
+                           cudaStream_t st) {
+  static bool once = false;
+  int rc;
+  if (!once) {
+    if ((rc = set_smem(mvf_fwd_resident_kernel<PASS_STATS, T>, kSmemLimit))) return rc;
+    if ((rc = set_smem(mvf_fwd_resident_kernel<PASS_TRAIN, T>, kSmemLimit))) return rc;
+    if ((rc = set_smem(mvf_fwd_resident_kernel<PASS_APPLY, T>, kSmemLimit))) return rc;
+    once = true;
+  }
+  const dim3 grid(d->N * (d->Cs / a.g.Cg));
+  if (d->use_hs && d->training) {
+    mvf_fwd_resident_kernel<PASS_STATS, T><<<grid, kThreads, smem, st>>>(tmx, a);
+    count_launch();
+    MVFB_LAUNCH_CHECK();
+    mvf_fwd_resident_kernel<PASS_TRAIN, T><<<grid, kThreads, smem, st>>>(tmx, a);
+  } else {
+    mvf_fwd_resident_kernel<PASS_APPLY, T><<<grid, kThreads, smem, st>>>(tmx, a);
+  }
+  count_launch();
+  MVFB_LAUNCH_CHECK();
+  return MVFB_OK;
+}
+
 int mvf_fast_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_stride, const float* wt,
                  const float* wh, const float* ww, const float* gamma, const float* beta, float* rm, float* rv,
                  float* save_mean, float* save_rstd, void* ws, cudaStream_t st) {
   Geo g;
-  if (!choose_geo(d, false, g) || !aligned16(x) || !aligned16(y) || y_stride % 8 != 0) return MVFB_ERR_UNSUPPORTED;
+  size_t smem_res = 0;
+  const bool resident = choose_resident(d, g, smem_res);
+  if (!resident && !choose_geo(d, false, g)) return MVFB_ERR_UNSUPPORTED;
+  if (!aligned16(x) || !aligned16(y) || y_stride % 8 != 0) return MVFB_ERR_UNSUPPORTED;
   CUtensorMap tmx;
   int rc = make_tmap(&tmx, x, d->C, g, true);
   if (rc) return rc;
@@ -775,6 +1055,11 @@ int mvf_fast_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_str
   a.save_mean = save_mean; a.save_rstd = save_rstd;
   a.partials = (float*)ws;
   a.y = (__nv_bfloat16*)y; a.y_pix = y_stride;
+  if (resident) {
+    if (d->T == 4) return launch_resident<4>(d, tmx, a, smem_res, st);
+    if (d->T == 8) return launch_resident<8>(d, tmx, a, smem_res, st);
+    return launch_resident<16>(d, tmx, a, smem_res, st);
+  }
   const size_t smem = fwd_smem(g);
   const dim3 grid(d->N * (d->Cs / g.Cg));
   if (d->use_hs && d->training) {

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--clips", default="12,32,64,128")
     ap.add_argument("--T", default="8")
     ap.add_argument("--no-flush", action="store_true")
+    ap.add_argument("--only-C", type=int, default=0, help="restrict to the slab shape with this C")
     args = ap.parse_args()
     peak = 6453.4
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -33,6 +34,8 @@ def main():
     rows = []
     for T in [int(v) for v in args.T.split(",")]:
         for (C, H, Cs) in [(512, 28, 64), (1024, 14, 128), (2048, 7, 256)]:
+            if args.only_C and C != args.only_C:
+                continue
             for B in [int(v) for v in args.clips.split(",")]:
                 for training in (True, False):
                     m = MVF(torch.nn.Identity(), T, C, alpha=0.125).cuda().train(training)
