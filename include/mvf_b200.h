@@ -84,12 +84,69 @@ int mvf_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_stride, 
  * Outputs dwt/dwh/dww (Cs,3) fp32, dgamma/dbeta (Cs) fp32 are OVERWRITTEN.  With share (wh==wt and/or
  * ww==wt) the views' tap gradients are summed into dwt and dwh/dww may be NULL.
  * training: save_mean/save_rstd from the forward; eval: running stats.
+ * dx MAY alias g (same pointer and stride): every kernel reads a frame of g completely before that frame's
+ * dx is written -- this is how the caller turns "dL/dx' for all C channels" into dL/dx in place.
  */
 int mvf_bwd(const mvfb_mvf_desc* d, const void* g, long long g_stride, const void* x, void* dx, long long dx_stride,
             const float* wt, const float* wh, const float* ww, const float* gamma, const float* beta,
             const float* running_mean, const float* running_var, const float* save_mean, const float* save_rstd,
             float* dwt, float* dwh, float* dww, float* dgamma, float* dbeta, void* workspace,
             size_t workspace_bytes, mvfb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * 1x1 convolution on NHWC bf16 activations as a tensor-core GEMM  --  replaces nn.Conv2d(kernel_size=1,
+ * bias=False) of Bottleneck.conv1 / conv3 / downsample (backbones/resnet.py:157-162,179-180,299-303) and
+ * the wrapped `self.net` of MVF.forward (MVF.py:138); called with (dY, W^T) it is also that layer's
+ * input-gradient.
+ *
+ *   D[m, n] = sum_{k <  K0} A0[m*lda0 + k] * B[n*ldb + k]
+ *           + sum_{k >= K0} A1[m*lda1 + k] * B[n*ldb + k]          m < M pixels, n < N, k < K
+ *
+ * A0 (optional, K0 > 0) is the compact MVF slab (F,H,W,Cs) written by mvf_fwd with y_stride = Cs; A1 is the
+ * block input x itself (its first K0 channels are simply never read): MVF.py:135-137's cat + contiguous
+ * never touch HBM.  All matrices bf16, K contiguous; accumulation fp32; D is rounded to bf16.
+ * colsum/colsq (both or neither; fp32 [N], zeroed by the caller) receive the per-output-channel sum and
+ * sum of squares of the ROUNDED D -- the batch statistics of the train-mode BatchNorm that follows.
+ * Requirements: K, K0 multiples of 64; N multiple of 64; leading dimensions multiples of 8; 16-byte aligned.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  long long M;                     /* rows = F*H*W pixels                                                */
+  int N, K, K0;                    /* output channels, input channels, channels taken from A0            */
+  long long lda0, lda1, ldb, ldd;  /* leading dimensions in elements                                     */
+} mvfb_gemm_desc;
+
+int conv1x1_gemm(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, void* out, float* colsum,
+                 float* colsq, mvfb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * BatchNorm2d (+ residual add) (+ ReLU) on NHWC bf16 activations viewed as (M = F*H*W, C) rows  --  replaces
+ * norm1+relu, norm2+relu, norm3 / downsample norm + `out += identity` + relu of Bottleneck.forward
+ * (backbones/resnet.py:213-242; nn.BatchNorm2d semantics as common/norm.py:66 builds it: eps 1e-5,
+ * momentum 0.1, biased variance to normalise, unbiased for the running estimate).
+ *
+ *   bn_stats : sums[0][c] = sum_m x[m,c], sums[1][c] = sum_m x[m,c]^2     (zeroes `sums` itself; the 1x1
+ *              GEMM can produce the same two rows in its epilogue, in which case this launch is skipped)
+ *   bn_apply : y = [relu]( gamma (x - mean) rstd + beta [+ residual] );  training: mean / var from `sums`,
+ *              save_mean/save_rstd written, running statistics updated in place; eval: running statistics
+ *   bn_bwd   : g = dL/dy.  g' = g * (y > 0) when relu;  dbeta = sum g', dgamma = sum g' xhat,
+ *              dx = gamma rstd (g' - dbeta/M - xhat dgamma/M)  (training)  or  gamma rstd g'  (eval);
+ *              dres (optional) = g' -- the gradient of the residual input.  `sums` is [2][C] scratch.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  long long M;       /* rows = F*H*W                          */
+  int C;             /* channels, multiple of 8, <= 2048      */
+  int relu;          /* 1: ReLU after the affine (+ residual)  */
+  int training;      /* 1: batch statistics                    */
+  float eps, momentum;
+} mvfb_bn_desc;
+
+int bn_stats(const mvfb_bn_desc* d, const void* x, long long ldx, float* sums, mvfb_stream_t stream);
+int bn_apply(const mvfb_bn_desc* d, const void* x, long long ldx, const void* residual, long long ldr, void* y,
+             long long ldy, const float* sums, const float* gamma, const float* beta, float* running_mean,
+             float* running_var, float* save_mean, float* save_rstd, mvfb_stream_t stream);
+int bn_bwd(const mvfb_bn_desc* d, const void* g, long long ldg, const void* y, long long ldy, const void* x,
+           long long ldx, const float* gamma, const float* mean, const float* rstd, void* dx, long long lddx,
+           void* dres, long long lddr, float* dgamma, float* dbeta, float* sums, mvfb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,291 @@
+// 1x1 convolution on NHWC activations == "TN" GEMM on the 5th-generation tensor cores:
+//
+//     D[m, n] = sum_k A[m, k] * B[n, k]        A: (M, K) pixels x input channels  (K contiguous, bf16)
+//                                               B: (N, K) output x input channels  (K contiguous, bf16)
+//                                               D: (M, N) pixels x output channels (N contiguous, bf16)
+//
+// Replaces nn.Conv2d(k=1, bias=False) of Bottleneck.conv1 / conv3 / downsample (backbones/resnet.py:157-180,
+// 299-303) and, called with (dY, W^T), its input-gradient.  The A operand may come from TWO tensors split
+// along K: columns [0, K0) from A0 (the compact MVF slab written by mvf_fwd) and [K0, K) from A1 (the
+// untouched channels of x), which is how MVF.forward's `torch.cat` + `.contiguous()` (MVF.py:135-137) are
+// eliminated: the concatenation happens in TMEM, never in HBM.
+//
+// Kernel: persistent, one CTA per SM, warp-specialised:
+//   warp 0   TMA producer   cp.async.bulk.tensor.2d, 128-byte swizzle, kStages-deep full/empty mbarrier ring
+//   warp 1   MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16),
+//                           fp32 accumulators in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i
+//                           overlaps the main loop of tile i+1; tcgen05.commit releases smem slots / signals TMEM
+//   warps 2-5 epilogue      tcgen05.ld 32x32b -> bf16 -> 128B-swizzled staging tile in smem -> per-column
+//                           (sum, sum of squares) of the ROUNDED outputs for the following train-mode BatchNorm
+//                           (one fp32 atomicAdd per column per tile) -> TMA store (clips the M tail)
+#include <cuda_bf16.h>
+
+#include "common.cuh"
+#include "mvf_internal.cuh"
+#include "ptx.cuh"
+
+namespace mvfb {
+
+namespace {
+
+constexpr int BM = 128;            // tile rows (UMMA M)
+constexpr int BK = 64;             // K per stage: 64 bf16 = 128 B = one swizzle atom
+constexpr int kThreads = 192;      // 6 warps
+constexpr int kEpiThreads = 128;
+
+struct GemmArgs {
+  long long M;
+  int N, K, K0;                    // K0: first K0 columns of A come from tensor map A0, the rest from A1
+  int m_tiles, n_tiles;
+  float* colsum;                   // [N] or null
+  float* colsq;                    // [N] or null
+};
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = BN >= 256 ? 3 : (BN >= 128 ? 5 : 6);
+  static constexpr int kABytes = BM * BK * 2;                 // 16 KB
+  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kPanels = BN / 64;                     // 64-column (128 B) panels of the output tile
+  static constexpr int kStagingBytes = BM * BN * 2;
+  static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN; // power of two >= 32: BN in {64,128,256} -> 128,256,512
+  static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + kStagingBytes + 256;
+};
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD, const GemmArgs a) {
+  using C = Cfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;                                        // kStages x [A tile | B tile]
+  uint8_t* staging = smem + (size_t)C::kStages * C::kStageBytes;     // BM x BN bf16, 64-column swizzled panels
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + C::kStagingBytes);
+  uint64_t* full = bars;                      // [kStages]
+  uint64_t* empty = bars + C::kStages;        // [kStages]
+  uint64_t* tmem_full = empty + C::kStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;       // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kblocks = a.K / BK;
+  const int total_tiles = a.m_tiles * a.n_tiles;
+
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&tmA0);
+    tma_prefetch_desc(&tmA1);
+    tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmD);
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full[s], 1);
+      mbar_init(&tmem_empty[s], kEpiThreads / 32);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, C::kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* sa = stage_base + (size_t)s * C::kStageBytes;
+          mbar_arrive_expect_tx(&full[s], C::kStageBytes);
+          const int k = kb * BK;
+          tma_load_2d(sa, k < a.K0 ? &tmA0 : &tmA1, &full[s], k, mt * BM);
+          tma_load_2d(sa + C::kABytes, &tmB, &full[s], k, nt * BN);
+          if (++s == C::kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+      int s = 0;
+      uint32_t ph = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_ph = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_ph ^ 1);               // epilogue has drained this accumulator
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(stage_base + (size_t)s * C::kStageBytes);
+          const uint32_t sb = sa + C::kABytes;
+#pragma unroll
+          for (int kk = 0; kk < BK / 16; ++kk) {
+            const uint64_t adesc = umma_smem_desc_sw128(sa + kk * 32, 0, 1024);
+            const uint64_t bdesc = umma_smem_desc_sw128(sb + kk * 32, 0, 1024);
+            umma_f16(d_tmem, adesc, bdesc, idesc, (kb | kk) != 0);
+          }
+          umma_commit(&empty[s]);                              // slot free once these MMAs have read it
+          if (++s == C::kStages) { s = 0; ph ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);                          // accumulator complete
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int et = threadIdx.x - 64;                           // 0..127
+    const int lane_grp = warp & 3;                             // TMEM lanes [32*lane_grp, +32) belong to this warp
+    const int row = lane_grp * 32 + lane;                      // output row within the tile
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+      const int acc = it & 1;
+      const uint32_t acc_ph = (it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc_fence_after();
+      // staging tile of the previous store must have been read by the TMA engine
+      if (et == 0) tma_store_wait_read<0>();
+      named_bar_sync(1, kEpiThreads);
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(lane_grp * 32) << 16);
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t v[32];
+        tmem_ld_32x32b_x32(taddr + c0, v);
+        tmem_ld_wait();
+        // 32 fp32 -> 32 bf16 = 64 B = four 16-byte chunks of this row in panel c0/64
+        uint8_t* panel = staging + (size_t)(c0 >> 6) * (BM * 128) + (size_t)row * 128;
+        const int chunk0 = (c0 & 63) >> 3;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          uint4 o;
+          o.x = pack_bf16(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+          o.y = pack_bf16(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+          o.z = pack_bf16(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+          o.w = pack_bf16(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+          *reinterpret_cast<uint4*>(panel + (((chunk0 + q) ^ (row & 7)) << 4)) = o;
+        }
+      }
+      // TMEM accumulator fully read: hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      fence_proxy_async_smem();                                // staging writes -> visible to the TMA engine
+      named_bar_sync(1, kEpiThreads);
+      if (et == 0) {
+#pragma unroll
+        for (int p = 0; p < C::kPanels; ++p) tma_store_2d(&tmD, staging + (size_t)p * (BM * 128), nt * BN + p * 64, mt * BM);
+        tma_store_commit();
+      }
+      // per-column statistics of the rounded tile (rows beyond M were zero-filled by TMA: they add nothing)
+      if (a.colsum) {
+        for (int col = et; col < BN; col += kEpiThreads) {
+          const uint8_t* panel = staging + (size_t)(col >> 6) * (BM * 128);
+          const int chunk = (col & 63) >> 3, within = (col & 7) * 2;
+          float s1 = 0.f, s2 = 0.f;
+#pragma unroll 8
+          for (int r = 0; r < BM; ++r) {
+            const __nv_bfloat16 h = *reinterpret_cast<const __nv_bfloat16*>(panel + r * 128 + ((chunk ^ (r & 7)) << 4) + within);
+            const float f = __bfloat162float(h);
+            s1 += f;
+            s2 = fmaf(f, f, s2);
+          }
+          atomicAdd(&a.colsum[nt * BN + col], s1);
+          atomicAdd(&a.colsq[nt * BN + col], s2);
+        }
+      }
+    }
+    if (et == 0) tma_store_wait<0>();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::kTmemCols);
+  }
+}
+
+int make_2d_map(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, uint64_t ld_elems, uint32_t box_cols,
+                uint32_t box_rows) {
+  const uint64_t dims[2] = {cols, rows};
+  const uint64_t strides[1] = {ld_elems * 2};
+  const uint32_t box[2] = {box_cols, box_rows};
+  return encode_tmap(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, nullptr,
+                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
+}
+
+template <int BN>
+int launch(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, void* out, float* colsum,
+           float* colsq, cudaStream_t st) {
+  using C = Cfg<BN>;
+  CUtensorMap tmA0, tmA1, tmB, tmD;
+  int rc;
+  // A1 is addressed with the GEMM's own k coordinate, so its map spans columns [0, K) of the source rows
+  if ((rc = make_2d_map(&tmA1, a1, (uint64_t)d->K, (uint64_t)d->M, (uint64_t)d->lda1, BK, BM))) return rc;
+  if (d->K0 > 0) {
+    if ((rc = make_2d_map(&tmA0, a0, (uint64_t)d->K0, (uint64_t)d->M, (uint64_t)d->lda0, BK, BM))) return rc;
+  } else {
+    tmA0 = tmA1;
+  }
+  if ((rc = make_2d_map(&tmB, b, (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldb, BK, BN))) return rc;
+  if ((rc = make_2d_map(&tmD, out, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldd, 64, BM))) return rc;
+  GemmArgs a;
+  a.M = d->M; a.N = d->N; a.K = d->K; a.K0 = d->K0;
+  a.m_tiles = (int)((d->M + BM - 1) / BM);
+  a.n_tiles = d->N / BN;
+  a.colsum = colsum; a.colsq = colsq;
+  static bool once = false;
+  if (!once) {
+    MVFB_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+    once = true;
+  }
+  int grid = a.m_tiles * a.n_tiles;
+  if (grid > num_sms()) grid = num_sms();
+  gemm_tn_kernel<BN><<<grid, kThreads, C::kSmem, st>>>(tmA0, tmA1, tmB, tmD, a);
+  count_launch();
+  MVFB_LAUNCH_CHECK();
+  return MVFB_OK;
+}
+
+}  // namespace
+
+}  // namespace mvfb
+
+using namespace mvfb;
+
+extern "C" int conv1x1_gemm(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, void* out,
+                            float* colsum, float* colsq, mvfb_stream_t stream) {
+  MVFB_CHECK(d && a1 && b && out, MVFB_ERR_ARG, "null descriptor / operand");
+  MVFB_CHECK(d->M > 0 && d->N > 0 && d->K > 0, MVFB_ERR_ARG, "bad GEMM shape M=%lld N=%d K=%d", d->M, d->N, d->K);
+  MVFB_CHECK(d->K % BK == 0 && d->K0 % BK == 0 && d->K0 >= 0 && d->K0 < d->K, MVFB_ERR_UNSUPPORTED,
+             "K=%d and K0=%d must be multiples of %d with K0 < K", d->K, d->K0, BK);
+  MVFB_CHECK(d->N % 64 == 0, MVFB_ERR_UNSUPPORTED, "N=%d must be a multiple of 64", d->N);
+  MVFB_CHECK(d->K0 == 0 || a0, MVFB_ERR_ARG, "K0 > 0 needs the A0 operand");
+  MVFB_CHECK((colsum == nullptr) == (colsq == nullptr), MVFB_ERR_ARG, "colsum and colsq go together");
+  MVFB_CHECK(d->lda1 % 8 == 0 && d->ldb % 8 == 0 && d->ldd % 8 == 0 && (d->K0 == 0 || d->lda0 % 8 == 0), MVFB_ERR_UNSUPPORTED,
+             "leading dimensions must be multiples of 8 elements (16 bytes)");
+  MVFB_CHECK(!((uintptr_t)a1 & 15) && !((uintptr_t)b & 15) && !((uintptr_t)out & 15) && !((uintptr_t)a0 & 15),
+             MVFB_ERR_UNSUPPORTED, "operands must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->N % 256 == 0) return launch<256>(d, a0, a1, b, out, colsum, colsq, st);
+  if (d->N % 128 == 0) return launch<128>(d, a0, a1, b, out, colsum, colsq, st);
+  return launch<64>(d, a0, a1, b, out, colsum, colsq, st);
+}

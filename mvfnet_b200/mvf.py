@@ -235,10 +235,8 @@ class MVF(nn.Module):
             cfg.momentum = float(bn.momentum)
         return cfg
 
-    def fuse(self, x):
-        """x' of MVF.py:137 (the tensor handed to self.net)."""
-        if self.num_shift_channel == 0:                                   # MVF.py:108
-            return x
+    def _kernel_args(self):
+        """(cfg, taps, BN tensors) in the form the C ABI takes them (fp32, share expressed by aliasing)."""
         cfg = self._cfg()
         wt, wh, ww = self._taps()
         bn = self.bn
@@ -250,13 +248,42 @@ class MVF(nn.Module):
         wt32, gamma32, beta32 = (t if t is None or t.dtype == torch.float32 else t.float() for t in (wt, gamma, beta))
         wh32 = wt32 if wh is wt else (wh if wh is None or wh.dtype == torch.float32 else wh.float())
         ww32 = wt32 if ww is wt else (ww if ww is None or ww.dtype == torch.float32 else ww.float())
-        y = _MVFFunction.apply(x, wt32, wh32, ww32, gamma32, beta32, rm, rv, cfg)
-        if cfg.use_hs and cfg.training and bn.track_running_stats:
-            bn.num_batches_tracked += 1
+        return cfg, wt32, wh32, ww32, gamma32, beta32, rm, rv
+
+    def _count_batch(self, cfg):
+        if cfg.use_hs and cfg.training and self.bn.track_running_stats:
+            self.bn.num_batches_tracked += 1
+
+    def fuse(self, x):
+        """x' of MVF.py:137 (the tensor handed to self.net)."""
+        if self.num_shift_channel == 0:                                   # MVF.py:108
+            return x
+        cfg, wt, wh, ww, gamma, beta, rm, rv = self._kernel_args()
+        y = _MVFFunction.apply(x, wt, wh, ww, gamma, beta, rm, rv, cfg)
+        self._count_batch(cfg)
         return y
 
-    def forward(self, x):
-        return self.net(self.fuse(x))
+    def forward(self, x, with_stats=False):
+        """MVF.forward(x) of the reference.  `with_stats=True` (used by Bottleneck's fused path only) also returns
+        the (2, Cout) per-channel sums of the output for the BatchNorm that follows, or None when the output was not
+        produced by the GEMM path."""
+        out = self._forward(x, with_stats)
+        if with_stats:
+            return out if isinstance(out, tuple) else (out, None)
+        return out
+
+    def _forward(self, x, with_stats):
+        net = self.net
+        if (self.num_shift_channel != 0 and self.num_shift_channel % 64 == 0 and isinstance(net, nn.Conv2d)
+                and net.kernel_size == (1, 1) and net.stride == (1, 1) and net.bias is None and net.groups == 1):
+            from . import ops
+            if ops.eligible(x, net.in_channels, net.out_channels):
+                # MVF kernel -> compact slab; tcgen05 GEMM with a K-split A operand (slab | untouched channels of x)
+                cfg, wt, wh, ww, gamma, beta, rm, rv = self._kernel_args()
+                out = ops.mvf_conv1x1(x, net.weight, wt, wh, ww, gamma, beta, rm, rv, cfg, stats=with_stats)
+                self._count_batch(cfg)
+                return out
+        return net(self.fuse(x))
 
 
 def make_multi_view_fusion(net, n_segment, alpha, mvf_freq=(1, 1, 1, 1), use_hs=True, share=False, mode='THW'):

@@ -1,0 +1,273 @@
+"""Host-side wrappers (autograd Functions over the C ABI) for the bottleneck's 1x1 convolutions.
+
+`conv1x1(x, weight)` replaces `nn.Conv2d(kernel_size=1, bias=False)` of Bottleneck.conv1 / conv3 /
+downsample (backbones/resnet.py:157-162,179-180,299-303) for bf16 channels_last activations;
+`mvf_conv1x1(x, mvf)` is MVF.forward as a whole (MVF.py:104-138): the fused MVF kernel writes only the compact
+slab and the GEMM reads its A operand from two tensors, so the reference's cat / contiguous copies never exist.
+Forward and input-gradient run on libmvf_b200's tcgen05 GEMM (`conv1x1_gemm`); the weight-gradient is still a
+library GEMM (torch.matmul) this round -- see DESIGN.md "gaps".
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+from . import _lib
+from ._lib import ptr
+from . import mvf as _mvf
+
+
+class GemmDesc(C.Structure):
+    """mvfb_gemm_desc (include/mvf_b200.h)."""
+    _fields_ = [("M", C.c_longlong), ("N", C.c_int), ("K", C.c_int), ("K0", C.c_int),
+                ("lda0", C.c_longlong), ("lda1", C.c_longlong), ("ldb", C.c_longlong), ("ldd", C.c_longlong)]
+
+
+class BnDesc(C.Structure):
+    """mvfb_bn_desc (include/mvf_b200.h)."""
+    _fields_ = [("M", C.c_longlong), ("C", C.c_int), ("relu", C.c_int), ("training", C.c_int),
+                ("eps", C.c_float), ("momentum", C.c_float)]
+
+
+_declared = False
+_VP, _LL = C.c_void_p, C.c_longlong
+
+
+def _L():
+    global _declared
+    L = _lib.lib()
+    if not _declared:
+        L.conv1x1_gemm.restype = C.c_int
+        L.conv1x1_gemm.argtypes = [C.POINTER(GemmDesc), _VP, _VP, _VP, _VP, _VP, _VP, _VP]
+        L.bn_stats.restype = C.c_int
+        L.bn_stats.argtypes = [C.POINTER(BnDesc), _VP, _LL, _VP, _VP]
+        L.bn_apply.restype = C.c_int
+        L.bn_apply.argtypes = [C.POINTER(BnDesc), _VP, _LL, _VP, _LL, _VP, _LL, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]
+        L.bn_bwd.restype = C.c_int
+        L.bn_bwd.argtypes = [C.POINTER(BnDesc), _VP, _LL, _VP, _LL, _VP, _LL, _VP, _VP, _VP, _VP, _LL, _VP, _LL, _VP,
+                             _VP, _VP, _VP]
+        _declared = True
+    return L
+
+
+def enabled() -> bool:
+    """MVFB_CONV1X1=0 routes the 1x1 convolutions back through torch / cuDNN (A/B measurements only)."""
+    return os.environ.get("MVFB_CONV1X1", "1") != "0"
+
+
+def _rows(t):
+    """(F, C, H, W) channels_last tensor -> its (F*H*W, C) row-major view (no copy)."""
+    f, c, h, w = t.shape
+    return t.permute(0, 2, 3, 1).reshape(f * h * w, c)
+
+
+def eligible(x, cin, cout):
+    return (enabled() and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and cin % 64 == 0 and cout % 64 == 0
+            and x.is_contiguous(memory_format=torch.channels_last) and x.shape[1] == cin)
+
+
+def gemm_tn(a1, b, a0=None, k0=0, stats=False, out=None):
+    """out[m, n] = sum_k A[m, k] b[n, k] with A = [a0[:, :k0] | a1[:, k0:]]; 2-D bf16 tensors whose last dim is
+    contiguous.  Returns (out, colsum, colsq) -- the sums are None unless `stats`."""
+    L = _L()
+    m, k = a1.shape
+    n = b.shape[0]
+    assert b.shape[1] == k and a1.stride(1) == 1 and b.stride(1) == 1
+    if out is None:
+        out = torch.empty((m, n), dtype=torch.bfloat16, device=a1.device)
+    d = GemmDesc()
+    d.M, d.N, d.K, d.K0 = m, n, k, k0
+    d.lda1, d.ldb, d.ldd = a1.stride(0), b.stride(0), out.stride(0)
+    d.lda0 = a0.stride(0) if a0 is not None else 0
+    colsum = colsq = None
+    if stats:
+        sums = torch.zeros((2, n), dtype=torch.float32, device=a1.device)
+        colsum, colsq = sums[0], sums[1]
+    rc = L.conv1x1_gemm(C.byref(d), ptr(a0), ptr(a1), ptr(b), ptr(out), ptr(colsum), ptr(colsq),
+                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    _lib.check(rc, "conv1x1_gemm")
+    return out, colsum, colsq
+
+
+def _nhwc_from_rows(rows, f, h, w):
+    return rows.view(f, h, w, rows.shape[1]).permute(0, 3, 1, 2)
+
+
+class _Conv1x1(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, stats):
+        f, cin, h, w = x.shape
+        wb = weight.detach().reshape(weight.shape[0], cin).to(torch.bfloat16)
+        out, colsum, _ = gemm_tn(_rows(x), wb, stats=stats)
+        ctx.save_for_backward(x, wb)
+        y = _nhwc_from_rows(out, f, h, w)
+        if not stats:
+            return y
+        sums = colsum._base if colsum._base is not None else colsum     # the (2, N) buffer
+        ctx.mark_non_differentiable(sums)
+        return y, sums
+
+    @staticmethod
+    def backward(ctx, g, *unused):
+        x, wb = ctx.saved_tensors
+        f, cin, h, w = x.shape
+        g = g.contiguous(memory_format=torch.channels_last)
+        g2 = _rows(g)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dx2, _, _ = gemm_tn(g2, wb.t().contiguous())               # dX = dY W  ==  TN GEMM against W^T
+            dx = _nhwc_from_rows(dx2, f, h, w)
+        if ctx.needs_input_grad[1]:
+            dw = torch.matmul(g2.t(), _rows(x)).float().view(wb.shape[0], cin, 1, 1)
+        return dx, dw, None
+
+
+def conv1x1(x, weight, stats=False):
+    """1x1 stride-1 bias-free convolution of a bf16 channels_last tensor on the tcgen05 GEMM.  With `stats` also
+    returns the (2, Cout) per-channel (sum, sum of squares) of the output, accumulated in the GEMM epilogue."""
+    return _Conv1x1.apply(x, weight, stats)
+
+
+class _MVFConv1x1(torch.autograd.Function):
+    """MVF.forward (MVF.py:104-138) in two launches: fused MVF kernel -> compact slab; K-split GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, weight, wt, wh, ww, gamma, beta, running_mean, running_var, cfg, stats):
+        f, c, h, w = x.shape
+        slab, xk, layout, save_mean, save_rstd = _mvf.mvf_slab_forward(
+            x, cfg, wt, wh, ww, gamma, beta, running_mean, running_var, out="slab")
+        wb = weight.detach().reshape(weight.shape[0], c).to(torch.bfloat16)
+        out, colsum, _ = gemm_tn(_rows(xk), wb, a0=_rows(slab), k0=cfg.Cs, stats=stats)
+        ctx.cfg, ctx.layout = cfg, layout
+        ctx.save_for_backward(xk, slab, wb, wt, wh, ww, gamma, beta, running_mean, running_var, save_mean, save_rstd)
+        y = _nhwc_from_rows(out, f, h, w)
+        if not stats:
+            return y
+        sums = colsum._base if colsum._base is not None else colsum
+        ctx.mark_non_differentiable(sums)
+        return y, sums
+
+    @staticmethod
+    def backward(ctx, g, *unused):
+        L = _lib.lib()
+        cfg, layout = ctx.cfg, ctx.layout
+        xk, slab, wb, wt, wh, ww, gamma, beta, running_mean, running_var, save_mean, save_rstd = ctx.saved_tensors
+        f, c, h, w = xk.shape
+        cs = cfg.Cs
+        g = g.contiguous(memory_format=torch.channels_last)
+        g2 = _rows(g)
+        # dL/dx' (all C channels) = dY W; the slab columns are then rewritten IN PLACE by mvf_bwd, which reads a
+        # frame of g completely before it writes that frame's dx (kernel contract, include/mvf_b200.h)
+        dxp, _, _ = gemm_tn(g2, wb.t().contiguous())
+        dw = None
+        if ctx.needs_input_grad[1]:
+            gt = g2.t()
+            dw = torch.cat([torch.matmul(gt, _rows(slab)), torch.matmul(gt, _rows(xk)[:, cs:])], dim=1)
+            dw = dw.float().view(wb.shape[0], c, 1, 1)
+        dx = _nhwc_from_rows(dxp, f, h, w)
+        d = _mvf._make_desc(xk, layout, cfg)
+        dev = xk.device
+        dwt = torch.empty((cs, 3), dtype=torch.float32, device=dev)
+        dwh = torch.empty_like(dwt) if (wh is not None and wh.data_ptr() != wt.data_ptr()) else None
+        dww = torch.empty_like(dwt) if (ww is not None and ww.data_ptr() != wt.data_ptr()) else None
+        dgamma = torch.empty(cs, dtype=torch.float32, device=dev) if cfg.use_hs else None
+        dbeta = torch.empty_like(dgamma) if cfg.use_hs else None
+        nbytes = L.mvf_bwd_workspace_bytes(C.byref(d))
+        ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        with _mvf._Timed("mvf_bwd", f * cs * h * w, xk.element_size()):
+            rc = L.mvf_bwd(C.byref(d), ptr(dxp), c, ptr(xk), ptr(dxp), c, ptr(wt), ptr(wh), ptr(ww), ptr(gamma),
+                           ptr(beta), ptr(running_mean), ptr(running_var), ptr(save_mean), ptr(save_rstd), ptr(dwt),
+                           ptr(dwh), ptr(dww), ptr(dgamma), ptr(dbeta), ptr(ws), ws.numel(), _mvf._stream())
+        _lib.check(rc, "mvf_bwd")
+        return dx, dw, dwt, dwh, dww, dgamma, dbeta, None, None, None, None
+
+
+def mvf_conv1x1(x, weight, wt, wh, ww, gamma, beta, running_mean, running_var, cfg, stats=False):
+    return _MVFConv1x1.apply(x, weight, wt, wh, ww, gamma, beta, running_mean, running_var, cfg, stats)
+
+
+# ------------------------------------------------------------------------------------------------ BatchNorm
+def bn_enabled() -> bool:
+    """MVFB_BN=0 routes BatchNorm / ReLU / residual back through torch (A/B measurements only)."""
+    return os.environ.get("MVFB_BN", "1") != "0"
+
+
+def bn_eligible(x, bn):
+    return (bn_enabled() and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and type(bn) is torch.nn.BatchNorm2d
+            and bn.affine and x.shape[1] % 8 == 0 and x.shape[1] <= 2048
+            and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class _BNAct(torch.autograd.Function):
+    """y = [relu](BatchNorm2d(x) [+ residual]) on bf16 channels_last tensors (bn_stats / bn_apply / bn_bwd)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, residual, sums, relu, training, eps, momentum):
+        L = _L()
+        f, c, h, w = x.shape
+        xr = _rows(x)
+        d = BnDesc()
+        d.M, d.C, d.relu, d.training, d.eps, d.momentum = xr.shape[0], c, int(relu), int(training), eps, momentum
+        dev = x.device
+        y = torch.empty((f, h, w, c), dtype=torch.bfloat16, device=dev)
+        save = torch.empty((2, c), dtype=torch.float32, device=dev)
+        if training and sums is None:
+            sums = torch.empty((2, c), dtype=torch.float32, device=dev)
+            _lib.check(L.bn_stats(C.byref(d), ptr(xr), xr.stride(0), ptr(sums), _stream()), "bn_stats")
+        rr = _rows(residual) if residual is not None else None
+        g32 = gamma if gamma.dtype == torch.float32 else gamma.float()
+        b32 = beta if beta.dtype == torch.float32 else beta.float()
+        rc = L.bn_apply(C.byref(d), ptr(xr), xr.stride(0), ptr(rr), rr.stride(0) if rr is not None else 0, ptr(y), c,
+                        ptr(sums), ptr(g32), ptr(b32), ptr(running_mean), ptr(running_var), ptr(save[0]), ptr(save[1]),
+                        _stream())
+        _lib.check(rc, "bn_apply")
+        yv = y.permute(0, 3, 1, 2)
+        ctx.relu, ctx.training, ctx.has_res, ctx.eps = relu, training, residual is not None, eps
+        ctx.save_for_backward(x, yv if relu else None, g32, save)
+        return yv
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _L()
+        x, y, gamma, save = ctx.saved_tensors
+        f, c, h, w = x.shape
+        g = g.contiguous(memory_format=torch.channels_last)
+        gr, xr = _rows(g), _rows(x)
+        yr = _rows(y) if y is not None else None
+        d = BnDesc()
+        d.M, d.C, d.relu, d.training, d.eps, d.momentum = xr.shape[0], c, int(ctx.relu), int(ctx.training), ctx.eps, 0.0
+        dev = x.device
+        dx = torch.empty((f, h, w, c), dtype=torch.bfloat16, device=dev)
+        dres = torch.empty((f, h, w, c), dtype=torch.bfloat16, device=dev) if ctx.has_res else None
+        grads = torch.empty((2, c), dtype=torch.float32, device=dev)
+        scratch = torch.empty((2, c), dtype=torch.float32, device=dev)
+        rc = L.bn_bwd(C.byref(d), ptr(gr), gr.stride(0), ptr(yr), yr.stride(0) if yr is not None else 0, ptr(xr),
+                      xr.stride(0), ptr(gamma), ptr(save[0]), ptr(save[1]), ptr(dx), c, ptr(dres), c, ptr(grads[0]),
+                      ptr(grads[1]), ptr(scratch), _stream())
+        _lib.check(rc, "bn_bwd")
+        dres_v = dres.permute(0, 3, 1, 2) if dres is not None else None
+        return dx.permute(0, 3, 1, 2), grads[0], grads[1], None, None, dres_v, None, None, None, None, None
+
+
+def bn_act(x, bn, relu=True, residual=None, sums=None):
+    """`bn` is the nn.BatchNorm2d that owns the parameters / running statistics (same semantics as calling it,
+    then adding `residual`, then ReLU)."""
+    training = bool(bn.training or not bn.track_running_stats)
+    rm = rv = None
+    momentum = 0.0
+    if bn.track_running_stats:
+        rm, rv = bn.running_mean, bn.running_var
+        if training:
+            momentum = 1.0 / float(int(bn.num_batches_tracked) + 1) if bn.momentum is None else float(bn.momentum)
+    if not training:
+        sums = None
+    y = _BNAct.apply(x, bn.weight, bn.bias, rm, rv, residual, sums, relu, training, float(bn.eps), momentum)
+    if training and bn.track_running_stats:
+        bn.num_batches_tracked += 1
+    return y

@@ -28,6 +28,38 @@ def constant_init(module, val, bias=0):
         nn.init.constant_(module.bias, bias)
 
 
+def _conv1x1(conv, x, want_stats=False):
+    """Run a 1x1 stride-1 nn.Conv2d (or the MVF wrapper around one) on the tcgen05 GEMM when the activation is
+    bf16 channels_last (the training / inference configuration); anything else (strided down-sampling, fp32
+    parity runs) is called as the module it is.  Returns (out, sums): `sums` is the (2, Cout) per-channel
+    (sum, sum of squares) accumulated by the GEMM epilogue, or None."""
+    from . import ops
+    from .mvf import MVF
+    if isinstance(conv, MVF):
+        return conv(x, with_stats=True) if want_stats else (conv(x), None)
+    if (type(conv) is nn.Conv2d and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.bias is None
+            and conv.groups == 1 and ops.eligible(x, conv.in_channels, conv.out_channels)):
+        if want_stats:
+            return ops.conv1x1(x, conv.weight, True)
+        return ops.conv1x1(x, conv.weight), None
+    return conv(x), None
+
+
+def _bn_act(bn, x, relu, residual=None, sums=None, relu_module=None):
+    """BatchNorm2d (+ residual) (+ ReLU): one fused kernel pair when eligible, the torch modules otherwise."""
+    from . import ops
+    if ops.bn_eligible(x, bn) and (residual is None or (residual.dtype == x.dtype and residual.shape == x.shape)):
+        if residual is not None:
+            residual = residual.contiguous(memory_format=torch.channels_last)
+        return ops.bn_act(x, bn, relu=relu, residual=residual, sums=sums)
+    out = bn(x)
+    if residual is not None:
+        out = out + residual
+    if relu:
+        out = relu_module(out) if relu_module is not None else torch.relu(out)
+    return out
+
+
 class Bottleneck(nn.Module):
     """1x1 -> 3x3 (stride) -> 1x1 (x4) residual block, style='pytorch' (resnet.py:104-244)."""
     expansion = 4
@@ -59,14 +91,16 @@ class Bottleneck(nn.Module):
 
     def forward(self, x):
         """resnet.py:208-244.  `self.conv1` is the MVF wrapper in the stages `mvf_freq` selects."""
+        fuse = x.is_cuda and x.dtype == torch.bfloat16
         identity = x
-        out = self.relu(self.norm1(self.conv1(x)))
-        out = self.relu(self.norm2(self.conv2(out)))
-        out = self.norm3(self.conv3(out))
+        out, sums = _conv1x1(self.conv1, x, fuse)
+        out = _bn_act(self.norm1, out, True, sums=sums, relu_module=self.relu)
+        out = _bn_act(self.norm2, self.conv2(out), True, relu_module=self.relu)
+        out, sums = _conv1x1(self.conv3, out, fuse)
         if self.downsample is not None:
-            identity = self.downsample(x)
-        out = out + identity
-        return self.relu(out)
+            ds, dsums = _conv1x1(self.downsample[0], x, fuse)
+            identity = _bn_act(self.downsample[1], ds, False, sums=dsums)
+        return _bn_act(self.norm3, out, True, residual=identity, sums=sums, relu_module=self.relu)
 
 
 def make_res_layer(block, inplanes, planes, blocks, stride=1, dilation=1, style='pytorch', norm_cfg=None,
@@ -146,7 +180,7 @@ class ResNet(nn.Module):
             raise TypeError('pretrained must be a str or None')
 
     def forward(self, x):
-        x = self.maxpool(self.relu(self.norm1(self.conv1(x))))
+        x = self.maxpool(_bn_act(self.norm1, self.conv1(x), True, relu_module=self.relu))
         outs = []
         for i, name in enumerate(self.res_layers):
             x = getattr(self, name)(x)

@@ -1,0 +1,137 @@
+"""GPU parity of the bottleneck operators behind the C ABI: the tcgen05 1x1-convolution GEMM (plain, K-split
+MVF variant, fused BatchNorm statistics), the fused BatchNorm(+residual)(+ReLU) kernels, and the whole fused
+Bottleneck against the same block executed by torch ops in fp32.  bf16 storage: tolerance 1e-2 relative."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import mvf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 128, 64), (4704, 512, 2048), (50176, 256, 1024), (12544, 2048, 512),
+                                   (1000, 64, 256), (129, 192, 128), (3136 * 4, 256, 64)])
+def test_gemm_tn_matches_fp32_matmul(M, N, K):
+    from mvfnet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    b = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    out, s1, s2 = ops.gemm_tn(a, b, stats=True)
+    ref = a.float() @ b.float().t()
+    assert rel(out, ref) < 1e-2
+    # the statistics are those of the ROUNDED output
+    assert rel(s1, out.float().sum(0)) < 1e-3 or float((s1 - out.float().sum(0)).abs().max()) < 1e-2 * float(out.float().abs().sum(0).max())
+    assert rel(s2, (out.float() ** 2).sum(0)) < 1e-3
+
+
+@pytest.mark.parametrize("M,N,K,K0", [(1568, 256, 512, 64), (3136, 512, 1024, 128), (392, 512, 2048, 256)])
+def test_gemm_k_split_operand(M, N, K, K0):
+    """A = [a0[:, :K0] | a1[:, K0:]]: the MVF concatenation without the copy (MVF.py:135)."""
+    from mvfnet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(K0)
+    a1 = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    a0 = torch.randn(M, K0, device="cuda", generator=g).bfloat16()
+    b = (torch.randn(N, K, device="cuda", generator=g) / K ** 0.5).bfloat16()
+    out, _, _ = ops.gemm_tn(a1, b, a0=a0, k0=K0)
+    cat = torch.cat([a0, a1[:, K0:]], dim=1).float()
+    assert rel(out, cat @ b.float().t()) < 1e-2
+
+
+def test_gemm_rejects_bad_shapes():
+    from mvfnet_b200 import ops, _lib
+    a = torch.zeros(128, 48, device="cuda", dtype=torch.bfloat16)
+    b = torch.zeros(64, 48, device="cuda", dtype=torch.bfloat16)
+    with pytest.raises(_lib.MvfB200Error):
+        ops.gemm_tn(a, b)                                       # K not a multiple of 64
+
+
+@pytest.mark.parametrize("C,HW,F", [(64, 56, 8), (256, 28, 8), (1024, 14, 16), (2048, 7, 24), (24, 5, 4)])
+@pytest.mark.parametrize("relu,res", [(True, False), (True, True), (False, False)])
+@pytest.mark.parametrize("training", [True, False])
+def test_bn_act_vs_oracle(C, HW, F, relu, res, training):
+    """oracle/mvf_oracle.py batchnorm2d(+relu+residual) forward and backward on the same bf16-rounded inputs."""
+    from mvfnet_b200 import ops
+    g = torch.Generator().manual_seed(C + HW)
+    bn = torch.nn.BatchNorm2d(C)
+    with torch.no_grad():
+        bn.weight.copy_(1 + 0.2 * torch.randn(C, generator=g))
+        bn.bias.copy_(0.3 * torch.randn(C, generator=g))
+        bn.running_mean.copy_(0.2 * torch.randn(C, generator=g))
+        bn.running_var.copy_(0.5 + torch.rand(C, generator=g))
+    rm0, rv0 = bn.running_mean.double().numpy().copy(), bn.running_var.double().numpy().copy()
+    bn = bn.cuda().train(training)
+    x = (torch.randn(F, C, HW, HW, generator=g) * 1.5 + 0.3).bfloat16()
+    r = torch.randn(F, C, HW, HW, generator=g).bfloat16() if res else None
+    gy = torch.randn(F, C, HW, HW, generator=g).bfloat16()
+    xd = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    rd = r.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True) if res else None
+    assert ops.bn_eligible(xd, bn)
+    y = ops.bn_act(xd, bn, relu=relu, residual=rd)
+    y.backward(gy.cuda().contiguous(memory_format=torch.channels_last))
+    gam, bet = bn.weight.detach().double().cpu().numpy(), bn.bias.detach().double().cpu().numpy()
+    xn = x.double().numpy()
+    a, st = O.batchnorm2d(xn, gam, bet, rm0, rv0, training)
+    pre = a + (r.double().numpy() if res else 0.0)
+    ref = O.relu(pre) if relu else pre
+    gref = gy.double().numpy() * ((pre > 0) if relu else 1.0)
+    dx, dg, db = O.batchnorm2d_backward(gref, xn, gam, st["mean"], st["rstd"], training)
+    t = lambda v: torch.as_tensor(np.asarray(v))
+    assert rel(y.detach().cpu(), t(ref)) < 1e-2
+    assert rel(xd.grad.cpu(), t(dx)) < 2e-2
+    assert rel(bn.weight.grad.cpu(), t(dg)) < 1e-2
+    assert rel(bn.bias.grad.cpu(), t(db)) < 1e-2
+    if res:
+        assert rel(rd.grad.cpu(), t(gref)) < 1e-2
+    if training:
+        assert rel(bn.running_mean.cpu(), t(st["new_running_mean"])) < 1e-3
+        assert rel(bn.running_var.cpu(), t(st["new_running_var"])) < 1e-3
+        assert int(bn.num_batches_tracked) == 1
+
+
+@pytest.mark.parametrize("inpl,planes,hw,stride,mvf", [(256, 64, 28, 1, False), (512, 256, 14, 1, True), (1024, 512, 14, 2, True),
+                                                        (64, 64, 28, 1, False)])
+def test_fused_bottleneck_vs_torch_fp32(inpl, planes, hw, stride, mvf):
+    """The fused block (MVF kernel + tcgen05 GEMMs + fused BN/ReLU/residual) against the SAME module run by torch
+    ops in fp32 (the path test_model_gpu pins to the reference's golden vectors)."""
+    import copy
+    import torch.nn as nn
+    from mvfnet_b200 import Bottleneck, MVF, _lib
+    torch.manual_seed(inpl + planes)
+    T, F = 4, 8
+    ds = None
+    if stride != 1 or inpl != planes * 4:
+        ds = nn.Sequential(nn.Conv2d(inpl, planes * 4, 1, stride, bias=False), nn.BatchNorm2d(planes * 4))
+    blk = Bottleneck(inpl, planes, stride, 1, ds)
+    if mvf:
+        blk.conv1 = MVF(blk.conv1, T, inpl, 0.125)
+    for m in blk.modules():
+        if isinstance(m, (nn.BatchNorm2d, nn.BatchNorm3d)):
+            with torch.no_grad():
+                m.weight.normal_(1, 0.2)
+                m.bias.normal_(0, 0.2)
+    blk = blk.cuda().train()
+    ref = copy.deepcopy(blk)
+    x = torch.randn(F, inpl, hw, hw, device="cuda")
+    gy = torch.randn(F, planes * 4, hw // stride, hw // stride, device="cuda")
+    xb = x.bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    before = _lib.launch_count()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        y = blk(xb)
+    y.backward(gy.bfloat16().contiguous(memory_format=torch.channels_last))
+    assert _lib.launch_count() - before >= 10, "fused kernels were not used"
+    xr = x.bfloat16().float().requires_grad_(True)
+    yr = ref(xr)
+    yr.backward(gy.bfloat16().float())
+    assert rel(y.detach().float(), yr.detach()) < 3e-2
+    assert rel(xb.grad.float(), xr.grad) < 5e-2
+    for (k, p), (_, q) in zip(blk.named_parameters(), ref.named_parameters()):
+        assert rel(p.grad.float(), q.grad) < 6e-2, k
+    for (k, b), (_, c) in zip(blk.named_buffers(), ref.named_buffers()):
+        if "running" in k:
+            assert rel(b.float(), c.float()) < 2e-2, k
