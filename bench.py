@@ -338,7 +338,8 @@ def main():
     ap.add_argument("--kernels-only", action="store_true",
                     help="profiling runs (ncu): skip the e2e loop and the cpu_baseline sample")
     args = ap.parse_args()
-    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "ours" and not args.kernels_only:
+        args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -15,6 +15,14 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
 
 
+def rel_l2(a, b):
+    """||a - b|| / ||b||: for gradients that passed through ReLU masks.  A bf16 and an fp32 pipeline legitimately
+    disagree on the mask of the few activations whose pre-activation is within rounding distance of 0, and each flip
+    changes that element's gradient by O(1); the max-norm is meaningless there, the energy norm is not."""
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm().clamp_min(1e-12))
+
+
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 128, 64), (4704, 512, 2048), (50176, 256, 1024), (12544, 2048, 512),
                                    (1000, 64, 256), (129, 192, 128), (3136 * 4, 256, 64)])
 def test_gemm_tn_matches_fp32_matmul(M, N, K):
@@ -96,9 +104,11 @@ def test_bn_act_vs_oracle(C, HW, F, relu, res, training):
 
 @pytest.mark.parametrize("inpl,planes,hw,stride,mvf", [(256, 64, 28, 1, False), (512, 256, 14, 1, True), (1024, 512, 14, 2, True),
                                                         (64, 64, 28, 1, False)])
-def test_fused_bottleneck_vs_torch_fp32(inpl, planes, hw, stride, mvf):
+def test_fused_bottleneck_vs_torch_fp32(inpl, planes, hw, stride, mvf, monkeypatch):
     """The fused block (MVF kernel + tcgen05 GEMMs + fused BN/ReLU/residual) against the SAME module run by torch
-    ops in fp32 (the path test_model_gpu pins to the reference's golden vectors)."""
+    ops in fp32 (the path test_model_gpu pins to the reference's golden vectors).  Three train-mode BatchNorms and
+    ReLU masks amplify bf16 rounding, so the yard-stick for the gradients is the error of torch's own bf16 autocast
+    execution of the block against the same fp32 run: the fused path must not be worse than 1.5x that."""
     import copy
     import torch.nn as nn
     from mvfnet_b200 import Bottleneck, MVF, _lib
@@ -116,22 +126,36 @@ def test_fused_bottleneck_vs_torch_fp32(inpl, planes, hw, stride, mvf):
                 m.weight.normal_(1, 0.2)
                 m.bias.normal_(0, 0.2)
     blk = blk.cuda().train()
-    ref = copy.deepcopy(blk)
+    ref, lib = copy.deepcopy(blk), copy.deepcopy(blk)
     x = torch.randn(F, inpl, hw, hw, device="cuda")
     gy = torch.randn(F, planes * 4, hw // stride, hw // stride, device="cuda")
-    xb = x.bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+
+    def run_bf16(module):
+        xb = x.bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = module(xb)
+        y.backward(gy.bfloat16().contiguous(memory_format=torch.channels_last))
+        return xb, y
+
     before = _lib.launch_count()
-    with torch.autocast("cuda", dtype=torch.bfloat16):
-        y = blk(xb)
-    y.backward(gy.bfloat16().contiguous(memory_format=torch.channels_last))
+    xb, y = run_bf16(blk)
     assert _lib.launch_count() - before >= 10, "fused kernels were not used"
+    monkeypatch.setenv("MVFB_CONV1X1", "0")
+    monkeypatch.setenv("MVFB_BN", "0")
+    xl, yl = run_bf16(lib)                                   # torch / cuDNN bf16 execution of the same block
+    monkeypatch.undo()
     xr = x.bfloat16().float().requires_grad_(True)
     yr = ref(xr)
     yr.backward(gy.bfloat16().float())
     assert rel(y.detach().float(), yr.detach()) < 3e-2
-    assert rel(xb.grad.float(), xr.grad) < 5e-2
-    for (k, p), (_, q) in zip(blk.named_parameters(), ref.named_parameters()):
-        assert rel(p.grad.float(), q.grad) < 6e-2, k
+
+    def check(ours, library, exact, what):
+        e_ours, e_lib = rel_l2(ours.float(), exact), rel_l2(library.float(), exact)
+        assert e_ours < max(1.5 * e_lib, 2e-2), (what, e_ours, e_lib)
+
+    check(xb.grad, xl.grad, xr.grad, "dx")
+    for (k, p), (_, q), (_, r) in zip(blk.named_parameters(), lib.named_parameters(), ref.named_parameters()):
+        check(p.grad, q.grad, r.grad, k)
     for (k, b), (_, c) in zip(blk.named_buffers(), ref.named_buffers()):
         if "running" in k:
             assert rel(b.float(), c.float()) < 2e-2, k
