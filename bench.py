@@ -198,8 +198,8 @@ def run_ours(args):
         with torch.autocast("cuda", dtype=torch.bfloat16):
             loss = model(img, label)["loss_cls"]
         loss.backward()
-        flat.check_views()
         if world > 1:
+            flat.gather()
             flat.allreduce_()
         torch.nn.utils.clip_grad_norm_(params, max_norm=40, norm_type=2)
         opt.step()
