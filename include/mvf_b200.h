@@ -140,6 +140,9 @@ typedef struct {
   float eps, momentum;
 } mvfb_bn_desc;
 
+/* y[r, 0:cols] = x[r, 0:cols] for r < M (bf16, 16-byte vectors): gathers / scatters a channel range of an
+ * NHWC tensor, e.g. the MVF slab; also the probe for what HBM sustains on that strided pattern. */
+int copy_cols(const void* x, long long ldx, void* y, long long ldy, long long M, int cols, mvfb_stream_t stream);
 int bn_stats(const mvfb_bn_desc* d, const void* x, long long ldx, float* sums, mvfb_stream_t stream);
 int bn_apply(const mvfb_bn_desc* d, const void* x, long long ldx, const void* residual, long long ldr, void* y,
              long long ldy, const float* sums, const float* gamma, const float* beta, float* running_mean,

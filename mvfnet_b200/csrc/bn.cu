@@ -259,6 +259,32 @@ bn_bwd_apply_kernel(const BwdArgs a) {
   }
 }
 
+// rows x cols strided 2-D copy in 16-byte vectors (cols % 8 == 0): y[r, :cols] = x[r, :cols]
+__global__ void __launch_bounds__(kThreads)
+copy_cols_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, __nv_bfloat16* __restrict__ y, long long ldy,
+                 long long M, int vecs) {
+  const long long total = M * vecs;
+  const long long stride = (long long)gridDim.x * kThreads;
+  long long i = (long long)blockIdx.x * kThreads + threadIdx.x;
+  for (; i + 3 * stride < total; i += 4 * stride) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long k = i + u * stride, r = k / vecs;
+      v[u] = ldg16(x + r * ldx + (k - r * vecs) * 8);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long k = i + u * stride, r = k / vecs;
+      *reinterpret_cast<uint4*>(y + r * ldy + (k - r * vecs) * 8) = v[u];
+    }
+  }
+  for (; i < total; i += stride) {
+    const long long r = i / vecs;
+    *reinterpret_cast<uint4*>(y + r * ldy + (i - r * vecs) * 8) = ldg16(x + r * ldx + (i - r * vecs) * 8);
+  }
+}
+
 int grid_for(long long M, int C) {
   const int vecs = C / 8;
   const int rows_par = kThreads / vecs;
@@ -292,6 +318,19 @@ bool ok16(const void* p, long long ld) { return ((uintptr_t)p & 15) == 0 && ld %
 using namespace mvfb;
 
 extern "C" {
+
+int copy_cols(const void* x, long long ldx, void* y, long long ldy, long long M, int cols, mvfb_stream_t stream) {
+  MVFB_CHECK(x && y && M > 0 && cols > 0 && cols % 8 == 0, MVFB_ERR_ARG, "bad copy_cols arguments");
+  MVFB_CHECK(ok16(x, ldx) && ok16(y, ldy), MVFB_ERR_UNSUPPORTED, "tensors must be 16-byte aligned with ld %% 8 == 0");
+  const int vecs = cols / 8;
+  long long blocks = (M * vecs + kThreads * 4 - 1) / (kThreads * 4);
+  const long long cap = (long long)num_sms() * 8;
+  if (blocks > cap) blocks = cap;
+  copy_cols_kernel<<<(int)blocks, kThreads, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, M, vecs);
+  count_launch();
+  MVFB_LAUNCH_CHECK();
+  return MVFB_OK;
+}
 
 int bn_stats(const mvfb_bn_desc* d, const void* x, long long ldx, float* sums, mvfb_stream_t stream) {
   int rc = check_bn(d);

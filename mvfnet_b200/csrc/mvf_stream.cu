@@ -18,6 +18,7 @@
 // writes one partial row per CTA; PASS_TRAIN reduces the rows of its channel group in its prologue while its
 // first loads are in flight.
 #include <cuda_bf16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "mvf_internal.cuh"
@@ -28,9 +29,18 @@ namespace mvfb {
 namespace {
 
 constexpr int kSmemLimit = 227 * 1024;
-constexpr int kMaxItems = 416;          // consumer threads per CTA (one item each); 14 warps = 4 per SM sub-partition (16K registers each) -> at most 128 registers per thread
-constexpr int kMaxThreads = kMaxItems + 32;
 constexpr int kMaxRing = 12;
+
+// Consumer threads per CTA (one item each).  V = channels per item.  V = 8: 13 + 1 warps = 4 per SM sub-partition
+// (16K registers each) -> at most 128 registers per thread (136 fails to launch: measured).  V = 4: half the
+// per-thread state, 25 + 1 warps at <= 72 registers -- twice the warps to hide latency with.
+template <int V>
+struct Lim {
+  static constexpr int kMaxItems = V == 8 ? 416 : 800;
+  static constexpr int kMaxThreads = kMaxItems + 32;
+};
+constexpr int kMaxThreadsAny = 832;
+constexpr int kMaxCWarps = 25;
 
 constexpr int PASS_APPLY = 0;   // eval-mode BN (running stats) or no BN at all
 constexpr int PASS_STATS = 1;   // train: partial sums only
@@ -38,12 +48,13 @@ constexpr int PASS_TRAIN = 2;   // train: batch statistics from the partials, th
 
 struct StreamGeo {
   int N, T, Cs, H, W;
-  int Cg, G, ngroups;     // channels per CTA, 8-channel vectors per pixel, channel groups
+  int V;                  // channels per item (8 or 4)
+  int Cg, G, ngroups;     // channels per CTA, V-channel vectors per pixel, channel groups
   int hsplit, Hs;         // H tiles and rows per tile
   int Hp, Wp;             // padded tile extents (Hs+2, W+2)
   int slot;               // bytes of one frame slot (multiple of 128)
   int R;                  // ring slots
-  int items;              // Hs*W*G  (<= kMaxItems)
+  int items;              // Hs*W*G  (<= Lim<V>::kMaxItems)
   int cwarps;             // consumer warps
   int P;                  // CTAs sharing one (channel group, H tile): clips are dealt round-robin
 };
@@ -51,6 +62,7 @@ struct StreamGeo {
 struct StreamArgs {
   StreamGeo g;
   int use_hs;
+  int debug;              // tuning experiments (MVFB_STREAM_DEBUG): 1 = no stores, 2 = no arithmetic / smem reads
   float eps, momentum;
   const float *wt, *wh, *ww, *gamma, *beta;
   float *running_mean, *running_var, *save_mean, *save_rstd;
@@ -59,36 +71,77 @@ struct StreamArgs {
   long long y_pix;
 };
 
-struct F8 {
-  float2 p[4];
+// V fp32 values as V/2 packed pairs (operands of FFMA2)
+template <int V>
+struct FV {
+  float2 p[V / 2];
 };
-__device__ __forceinline__ F8 zero8() {
-  F8 r;
+template <int V>
+__device__ __forceinline__ FV<V> zerov() {
+  FV<V> r;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) r.p[j] = make_float2(0.f, 0.f);
+  for (int j = 0; j < V / 2; ++j) r.p[j] = make_float2(0.f, 0.f);
   return r;
 }
-__device__ __forceinline__ F8 lds_unpack8(const uint8_t* ptr) {
-  const uint4 v = *reinterpret_cast<const uint4*>(ptr);
-  F8 r;
-  r.p[0] = make_float2(bf16_lo(v.x), bf16_hi(v.x));
-  r.p[1] = make_float2(bf16_lo(v.y), bf16_hi(v.y));
-  r.p[2] = make_float2(bf16_lo(v.z), bf16_hi(v.z));
-  r.p[3] = make_float2(bf16_lo(v.w), bf16_hi(v.w));
-  return r;
-}
-__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+// V bf16 values from shared memory (32-bit shared-space address), unpacked
+template <int V>
+__device__ __forceinline__ FV<V> lds_bf16(uint32_t addr);
+template <>
+__device__ __forceinline__ FV<8> lds_bf16<8>(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr));
-  return v;
-}
-__device__ __forceinline__ F8 unpack8(const uint4& v) {
-  F8 r;
+  FV<8> r;
   r.p[0] = make_float2(bf16_lo(v.x), bf16_hi(v.x));
   r.p[1] = make_float2(bf16_lo(v.y), bf16_hi(v.y));
   r.p[2] = make_float2(bf16_lo(v.z), bf16_hi(v.z));
   r.p[3] = make_float2(bf16_lo(v.w), bf16_hi(v.w));
   return r;
+}
+template <>
+__device__ __forceinline__ FV<4> lds_bf16<4>(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  FV<4> r;
+  r.p[0] = make_float2(bf16_lo(v.x), bf16_hi(v.x));
+  r.p[1] = make_float2(bf16_lo(v.y), bf16_hi(v.y));
+  return r;
+}
+template <int V>
+__device__ __forceinline__ FV<V> lds_f32(const float* p) {
+  FV<V> r;
+#pragma unroll
+  for (int j = 0; j < V / 4; ++j) {
+    const float4 a = *reinterpret_cast<const float4*>(p + 4 * j);
+    r.p[2 * j] = make_float2(a.x, a.y);
+    r.p[2 * j + 1] = make_float2(a.z, a.w);
+  }
+  return r;
+}
+template <int V>
+__device__ __forceinline__ void fmav(FV<V>& z, const FV<V>& k, const FV<V>& x) {
+#pragma unroll
+  for (int j = 0; j < V / 2; ++j) z.p[j] = __ffma2_rn(k.p[j], x.p[j], z.p[j]);
+}
+template <int V>
+__device__ __forceinline__ void store_bf16(__nv_bfloat16* dst, const FV<V>& z);
+template <>
+__device__ __forceinline__ void store_bf16<8>(__nv_bfloat16* dst, const FV<8>& z) {
+  uint4 o;
+  o.x = pack_bf16(z.p[0].x, z.p[0].y); o.y = pack_bf16(z.p[1].x, z.p[1].y);
+  o.z = pack_bf16(z.p[2].x, z.p[2].y); o.w = pack_bf16(z.p[3].x, z.p[3].y);
+  *reinterpret_cast<uint4*>(dst) = o;
+}
+template <>
+__device__ __forceinline__ void store_bf16<4>(__nv_bfloat16* dst, const FV<4>& z) {
+  uint2 o;
+  o.x = pack_bf16(z.p[0].x, z.p[0].y); o.y = pack_bf16(z.p[1].x, z.p[1].y);
+  *reinterpret_cast<uint2*>(dst) = o;
+}
+
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
 }
 __device__ __forceinline__ bool try_wait_u32(uint32_t bar, uint32_t parity) {
   uint32_t ok;
@@ -113,20 +166,9 @@ __device__ __forceinline__ void wait_u32(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void arrive_u32(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ F8 lds_f8(const float* p) {
-  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
-  F8 r;
-  r.p[0] = make_float2(a.x, a.y); r.p[1] = make_float2(a.z, a.w);
-  r.p[2] = make_float2(b.x, b.y); r.p[3] = make_float2(b.z, b.w);
-  return r;
-}
-__device__ __forceinline__ void fma8(F8& z, const F8& k, const F8& x) {
-#pragma unroll
-  for (int j = 0; j < 4; ++j) z.p[j] = __ffma2_rn(k.p[j], x.p[j], z.p[j]);
-}
 
-template <int PASS>
-__global__ void __launch_bounds__(kMaxThreads, 1)
+template <int PASS, int V>
+__global__ void __launch_bounds__(Lim<V>::kMaxThreads, 1)
 mvf_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const StreamArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const StreamGeo& g = a.g;
@@ -146,12 +188,13 @@ mvf_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const StreamArgs 
   float* s_coef = reinterpret_cast<float*>(slots + (size_t)g.R * g.slot);   // [7][Cg]
   float* s_scale = s_coef + 7 * g.Cg;                          // [Cg]
   float* s_shift = s_scale + g.Cg;                             // [Cg]
-  double* s_dpart = reinterpret_cast<double*>(s_shift + g.Cg); // [kMaxThreads]
-  double* s_dsum = s_dpart + kMaxThreads;                      // [2*Cg]
-  float* s_red = reinterpret_cast<float*>(s_dsum + 128);      // [cwarps][G][16]
-  float* s_out = s_red + 16 * 8 * 16;                          // [G][16]
+  double* s_dpart = reinterpret_cast<double*>(s_shift + g.Cg); // [kMaxThreadsAny]
+  double* s_dsum = s_dpart + kMaxThreadsAny;                   // [2*Cg]
+  float* s_red = reinterpret_cast<float*>(s_dsum + 128);      // [cwarps][2*Cg]
 
   const uint32_t frame_bytes = (uint32_t)(g.Hp * g.Wp * g.Cg * 2);
+  unsigned long long* stamps = reinterpret_cast<unsigned long long*>(a.partials) + (size_t)blockIdx.x * 4;
+  if ((a.debug & 4) && tid == 0) stamps[0] = gtimer();
   if (tid == 0) {
     tma_prefetch_desc(&tmx);
     for (int s = 0; s < g.R; ++s) {
@@ -173,20 +216,23 @@ mvf_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const StreamArgs 
     }
   }
 
-  // ---- per-channel constants, computed once per CTA
-  for (int i = tid; i < 7 * g.Cg; i += nthreads) {
-    const int q = i / g.Cg, ch = i - q * g.Cg, c3 = (c0 + ch) * 3;
-    float v;
-    switch (q) {
-      case 0: v = a.wt[c3 + 1] + (a.wh ? a.wh[c3 + 1] : 0.f) + (a.ww ? a.ww[c3 + 1] : 0.f); break;   // centre
-      case 1: v = a.wt[c3]; break;                                                                 // t-1
-      case 2: v = a.wt[c3 + 2]; break;                                                             // t+1
-      case 3: v = a.wh ? a.wh[c3] : 0.f; break;                                                    // h-1
-      case 4: v = a.wh ? a.wh[c3 + 2] : 0.f; break;                                                // h+1
-      case 5: v = a.ww ? a.ww[c3] : 0.f; break;                                                    // w-1
-      default: v = a.ww ? a.ww[c3 + 2] : 0.f; break;                                               // w+1
-    }
-    s_coef[i] = v;
+  // ---- per-channel constants, computed once per CTA.  All global loads are issued before the first use so the
+  // prologue costs one memory round trip, not three.
+  float bn_m = 0.f, bn_v = 1.f, bn_g = 1.f, bn_b = 0.f;
+  if (PASS == PASS_APPLY && a.use_hs && tid < g.Cg) {
+    bn_m = a.running_mean[c0 + tid]; bn_v = a.running_var[c0 + tid];
+    bn_g = a.gamma[c0 + tid]; bn_b = a.beta[c0 + tid];
+  }
+  if (PASS == PASS_TRAIN && tid < g.Cg) { bn_g = a.gamma[c0 + tid]; bn_b = a.beta[c0 + tid]; }
+  for (int i = tid; i < 3 * g.Cg; i += nthreads) {
+    // taps of view i / Cg: (w[0], w[1], w[2]) -> s_coef rows: centre accumulates all views' middle taps later
+    const int view = i / g.Cg, ch = i - view * g.Cg, c3 = (c0 + ch) * 3;
+    const float* wv = view == 0 ? a.wt : (view == 1 ? a.wh : a.ww);
+    float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+    if (wv) { w0 = wv[c3]; w1 = wv[c3 + 1]; w2 = wv[c3 + 2]; }
+    s_coef[(1 + 2 * view) * g.Cg + ch] = w0;                   // rows 1,3,5: t-1, h-1, w-1
+    s_coef[(2 + 2 * view) * g.Cg + ch] = w2;                   // rows 2,4,6: t+1, h+1, w+1
+    s_red[view * g.Cg + ch] = w1;                              // middle taps, summed below
   }
   if (PASS == PASS_TRAIN) {
     const int per = 2 * g.Cg, rows = g.hsplit * g.P;          // partial rows of this channel group
@@ -211,9 +257,9 @@ mvf_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const StreamArgs 
       double var = s_dsum[tid * 2 + 1] / m - mu * mu;
       if (var < 0) var = 0;
       const float mean = (float)mu, rstd = (float)(1.0 / sqrt(var + (double)a.eps));
-      const float sc = a.gamma[c] * rstd;
+      const float sc = bn_g * rstd;
       s_scale[tid] = sc;
-      s_shift[tid] = a.beta[c] - mean * sc;
+      s_shift[tid] = bn_b - mean * sc;
       if (rest == 0) {
         a.save_mean[c] = mean;
         a.save_rstd[c] = rstd;
@@ -229,9 +275,9 @@ mvf_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const StreamArgs 
       const int c = c0 + tid;
       float sc = 1.f, sh = 0.f;
       if (a.use_hs) {
-        const float mean = a.running_mean[c], rstd = 1.f / sqrtf(a.running_var[c] + a.eps);
-        sc = a.gamma[c] * rstd;
-        sh = a.beta[c] - mean * sc;
+        const float mean = bn_m, rstd = 1.f / sqrtf(bn_v + a.eps);
+        sc = bn_g * rstd;
+        sh = bn_b - mean * sc;
         if (rest == 0 && a.save_mean) { a.save_mean[c] = mean; a.save_rstd[c] = rstd; }
       }
       s_scale[tid] = sc;
@@ -239,9 +285,12 @@ mvf_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const StreamArgs 
     }
   }
   __syncthreads();
+  if (tid < g.Cg) s_coef[tid] = s_red[tid] + s_red[g.Cg + tid] + s_red[2 * g.Cg + tid];   // centre coefficient
+  __syncthreads();
 
-  F8 sum = zero8(), sq = zero8();
+  FV<V> sum = zerov<V>(), sq = zerov<V>();
   const int vec = tid % g.G;
+  if ((a.debug & 4) && tid == 0) stamps[1] = gtimer();
 
   if (producer) {
     // ===== TMA producer: refill slots as the consumers release them
@@ -258,124 +307,132 @@ mvf_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const StreamArgs 
       }
     }
   } else {
-    // ===== consumers: one (pixel, 8-channel vector) item per thread
-    const bool active = tid < g.items;
+    // ===== consumers: one (pixel, V-channel vector) item per thread
+    const bool active = tid < g.items && !(a.debug & 2);
     const int pix = tid / g.G;
     const int hl = pix / g.W, w = pix - hl * g.W;             // row within the H tile, column
     const int pixb = g.Cg * 2, rowb = g.Wp * pixb;
-    const int off = ((hl + 1) * g.Wp + (w + 1)) * pixb + vec * 16;
-    F8 kc = lds_f8(s_coef + vec * 8), kt0 = lds_f8(s_coef + g.Cg + vec * 8), kt2 = lds_f8(s_coef + 2 * g.Cg + vec * 8);
-    F8 kh0 = lds_f8(s_coef + 3 * g.Cg + vec * 8), kh2 = lds_f8(s_coef + 4 * g.Cg + vec * 8);
-    F8 kw0 = lds_f8(s_coef + 5 * g.Cg + vec * 8), kw2 = lds_f8(s_coef + 6 * g.Cg + vec * 8);
-    F8 scale = zero8(), shift = zero8();
-    if (PASS != PASS_STATS) { scale = lds_f8(s_scale + vec * 8); shift = lds_f8(s_shift + vec * 8); }
+    const int off = ((hl + 1) * g.Wp + (w + 1)) * pixb + vec * (2 * V);
+    const FV<V> kc = lds_f32<V>(s_coef + vec * V), kt0 = lds_f32<V>(s_coef + g.Cg + vec * V),
+                kt2 = lds_f32<V>(s_coef + 2 * g.Cg + vec * V), kh0 = lds_f32<V>(s_coef + 3 * g.Cg + vec * V),
+                kh2 = lds_f32<V>(s_coef + 4 * g.Cg + vec * V), kw0 = lds_f32<V>(s_coef + 5 * g.Cg + vec * V),
+                kw2 = lds_f32<V>(s_coef + 6 * g.Cg + vec * V);
+    FV<V> scale = zerov<V>(), shift = zerov<V>();
+    if (PASS != PASS_STATS) { scale = lds_f32<V>(s_scale + vec * V); shift = lds_f32<V>(s_shift + vec * V); }
     const bool hs_on = a.use_hs != 0;
     const size_t frame_elems = (size_t)g.H * g.W * a.y_pix;
-    const size_t ypix = ((size_t)(h0 + hl) * g.W + w) * a.y_pix + c0 + vec * 8;
+    const size_t ypix = ((size_t)(h0 + hl) * g.W + w) * a.y_pix + c0 + vec * V;
     // 32-bit shared-space addresses keep the per-frame bookkeeping to a handful of integer instructions
     const uint32_t full0 = smem_u32(full), empty0 = smem_u32(empty);
     const uint32_t base = smem_u32(slots) + (uint32_t)off;
     const uint32_t slotb = (uint32_t)g.slot, ringb = (uint32_t)g.R * slotb;
 
     uint32_t cur = base, fb = full0, ph = 0;                   // current frame: slot address, full barrier, parity
+    __nv_bfloat16* yp = a.y;
+    // one frame step; (xm, xc, xp) = centre values of frames t-1, t, t+1.  The caller rotates the three register
+    // sets instead of moving them (3-way unrolled frame loop).
+    auto step = [&](const FV<V>& xm, const FV<V>& xc, FV<V>& xp, int t) {
+      uint32_t nxt = cur + slotb, fb1 = fb + 8, ph1 = ph;
+      if (nxt == base + ringb) { nxt = base; fb1 = full0; ph1 ^= 1; }
+      xp = zerov<V>();
+      if (t + 1 < g.T) {
+        wait_u32(fb1, ph1);
+        if (active) xp = lds_bf16<V>(nxt);
+      }
+      if (active) {
+        FV<V> z;
+#pragma unroll
+        for (int j = 0; j < V / 2; ++j) z.p[j] = __fmul2_rn(kc.p[j], xc.p[j]);
+        fmav<V>(z, kt0, xm);
+        fmav<V>(z, kt2, xp);
+        fmav<V>(z, kh0, lds_bf16<V>(cur - rowb));
+        fmav<V>(z, kh2, lds_bf16<V>(cur + rowb));
+        fmav<V>(z, kw0, lds_bf16<V>(cur - pixb));
+        fmav<V>(z, kw2, lds_bf16<V>(cur + pixb));
+        if (PASS == PASS_STATS) {
+#pragma unroll
+          for (int j = 0; j < V / 2; ++j) {
+            sum.p[j] = __fadd2_rn(sum.p[j], z.p[j]);
+            sq.p[j] = __ffma2_rn(z.p[j], z.p[j], sq.p[j]);
+          }
+        } else {
+          if (hs_on) {
+#pragma unroll
+            for (int j = 0; j < V / 2; ++j) {
+              const float2 u = __ffma2_rn(z.p[j], scale.p[j], shift.p[j]);
+              float2 sg;
+              sg.x = __saturatef(fmaf(u.x, 1.f / 6.f, 0.5f));
+              sg.y = __saturatef(fmaf(u.y, 1.f / 6.f, 0.5f));
+              z.p[j] = __fmul2_rn(u, sg);
+            }
+          }
+          if (!(a.debug & 1)) store_bf16<V>(yp, z);
+        }
+      }
+      yp += frame_elems;
+      __syncwarp();
+      if (lane == 0) arrive_u32(empty0 + (fb - full0));         // this warp is done with frame t's slot
+      cur = nxt;
+      fb = fb1;
+      ph = ph1;
+    };
     for (int kclip = 0; kclip < nclips; ++kclip) {
       const int n = p + kclip * g.P;
-      __nv_bfloat16* yp = a.y + (size_t)n * g.T * frame_elems + ypix;
-      F8 xm = zero8(), xc = zero8(), xp;
+      yp = a.y + (size_t)n * g.T * frame_elems + ypix;
+      FV<V> ra = zerov<V>(), rb = zerov<V>(), rc;
       wait_u32(fb, ph);
-      if (active) xc = unpack8(lds128(cur));
+      if ((a.debug & 4) && tid == 0 && kclip == 0) stamps[2] = gtimer();
+      if (active) rb = lds_bf16<V>(cur);
 #pragma unroll 1
-      for (int t = 0; t < g.T; ++t) {
-        uint32_t nxt = cur + slotb, fb1 = fb + 8, ph1 = ph;
-        if (nxt == base + ringb) { nxt = base; fb1 = full0; ph1 ^= 1; }
-        xp = zero8();
-        if (t + 1 < g.T) {
-          wait_u32(fb1, ph1);
-          if (active) xp = unpack8(lds128(nxt));
-        }
-        if (active) {
-          F8 z;
-#pragma unroll
-          for (int j = 0; j < 4; ++j) z.p[j] = __fmul2_rn(kc.p[j], xc.p[j]);
-          fma8(z, kt0, xm);
-          fma8(z, kt2, xp);
-          fma8(z, kh0, unpack8(lds128(cur - rowb)));
-          fma8(z, kh2, unpack8(lds128(cur + rowb)));
-          fma8(z, kw0, unpack8(lds128(cur - pixb)));
-          fma8(z, kw2, unpack8(lds128(cur + pixb)));
-          if (PASS == PASS_STATS) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              sum.p[j] = __fadd2_rn(sum.p[j], z.p[j]);
-              sq.p[j] = __ffma2_rn(z.p[j], z.p[j], sq.p[j]);
-            }
-          } else {
-            if (hs_on) {
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const float2 u = __ffma2_rn(z.p[j], scale.p[j], shift.p[j]);
-                float2 sg;
-                sg.x = __saturatef(fmaf(u.x, 1.f / 6.f, 0.5f));
-                sg.y = __saturatef(fmaf(u.y, 1.f / 6.f, 0.5f));
-                z.p[j] = __fmul2_rn(u, sg);
-              }
-            }
-            uint4 o;
-            o.x = pack_bf16(z.p[0].x, z.p[0].y); o.y = pack_bf16(z.p[1].x, z.p[1].y);
-            o.z = pack_bf16(z.p[2].x, z.p[2].y); o.w = pack_bf16(z.p[3].x, z.p[3].y);
-            *reinterpret_cast<uint4*>(yp) = o;
-          }
-        }
-        yp += frame_elems;
-        __syncwarp();
-        if (lane == 0) arrive_u32(empty0 + (fb - full0));       // this warp is done with frame t's slot
-        xm = xc;
-        xc = xp;
-        cur = nxt;
-        fb = fb1;
-        ph = ph1;
+      for (int t = 0; t < g.T; t += 3) {
+        step(ra, rb, rc, t);
+        if (t + 1 < g.T) step(rb, rc, ra, t + 1);
+        if (t + 2 < g.T) step(rc, ra, rb, t + 2);
       }
     }
   }
 
+  if ((a.debug & 4) && tid == 0) stamps[3] = gtimer();
   if (PASS == PASS_STATS) {
     // CTA reduction of (sum, sumsq) by channel vector: lanes with equal lane % G own the same channels
-    float acc[16];
+    float acc[2 * V];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < V / 2; ++j) {
       acc[2 * j] = sum.p[j].x; acc[2 * j + 1] = sum.p[j].y;
-      acc[8 + 2 * j] = sq.p[j].x; acc[8 + 2 * j + 1] = sq.p[j].y;
+      acc[V + 2 * j] = sq.p[j].x; acc[V + 2 * j + 1] = sq.p[j].y;
     }
 #pragma unroll
-    for (int q = 0; q < 16; ++q) {
+    for (int q = 0; q < 2 * V; ++q) {
       float v = acc[q];
       for (int o = 16; o >= g.G; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       acc[q] = v;
     }
     if (!producer && lane < g.G) {
 #pragma unroll
-      for (int q = 0; q < 16; ++q) s_red[(warp * g.G + lane) * 16 + q] = acc[q];
+      for (int q = 0; q < 2 * V; ++q) s_red[(warp * g.G + lane) * (2 * V) + q] = acc[q];
     }
     __syncthreads();
     for (int i = tid; i < 2 * g.Cg; i += nthreads) {
       const int ch = i >> 1, kind = i & 1;
-      const int idx = (ch / 8) * 16 + kind * 8 + (ch % 8);
+      const int idx = (ch / V) * (2 * V) + kind * V + (ch % V);
       float v = 0.f;
-      for (int wv = 0; wv < g.cwarps; ++wv) v += s_red[wv * g.G * 16 + idx];
+      for (int wv = 0; wv < g.cwarps; ++wv) v += s_red[wv * 2 * g.Cg + idx];
       a.partials[(size_t)blockIdx.x * 2 * g.Cg + i] = v;
     }
   }
-  (void)s_out;
 }
 
 size_t stream_smem(const StreamGeo& g) {
-  return 256 + (size_t)g.R * g.slot + (size_t)(7 + 2) * g.Cg * 4 + (size_t)kMaxThreads * 8 + 128 * 8 +
-         (size_t)16 * 8 * 16 * 4 + 8 * 16 * 4 + 64;
+  return 256 + (size_t)g.R * g.slot + (size_t)(7 + 2) * g.Cg * 4 + (size_t)kMaxThreadsAny * 8 + 128 * 8 +
+         (size_t)kMaxCWarps * 2 * g.Cg * 4 + 64;
 }
 
 bool choose_stream(const mvfb_mvf_desc* d, StreamGeo& g) {
   if (d->dtype != MVFB_BF16 || d->layout != MVFB_NHWC) return false;
   if (d->Cs % 8 != 0 || d->C % 8 != 0 || d->W + 2 > 256) return false;
+  static const int forcedV = getenv("MVFB_STREAM_V") ? atoi(getenv("MVFB_STREAM_V")) : 0;     // tuning experiments
+  const int V = forcedV == 4 || forcedV == 8 ? forcedV : 8;
+  const int max_items = V == 8 ? Lim<8>::kMaxItems : Lim<4>::kMaxItems;
   const int splits[4] = {1, 2, 4, 7};
   const int cands[4] = {64, 32, 16, 8};
   for (int si = 0; si < 4; ++si) {
@@ -386,10 +443,12 @@ bool choose_stream(const mvfb_mvf_desc* d, StreamGeo& g) {
     for (int ci = 0; ci < 4; ++ci) {
       const int Cg = cands[ci];
       if (d->Cs % Cg) continue;
-      const int items = Hs * d->W * (Cg / 8);
-      if (items > kMaxItems) continue;
+      const int G = Cg / V;
+      if (G > 16) continue;                                  // lanes sharing a vector must tile a warp
+      const int items = Hs * d->W * G;
+      if (items > max_items) continue;
       g.N = d->N; g.T = d->T; g.Cs = d->Cs; g.H = d->H; g.W = d->W;
-      g.Cg = Cg; g.G = Cg / 8; g.ngroups = d->Cs / Cg;
+      g.V = V; g.Cg = Cg; g.G = G; g.ngroups = d->Cs / Cg;
       g.hsplit = hsplit; g.Hs = Hs; g.Hp = Hs + 2; g.Wp = d->W + 2;
       g.slot = (g.Hp * g.Wp * Cg * 2 + 127) / 128 * 128;
       g.items = items;
@@ -408,6 +467,31 @@ bool choose_stream(const mvfb_mvf_desc* d, StreamGeo& g) {
     }
   }
   return false;
+}
+
+template <int V>
+int launch_stream(const mvfb_mvf_desc* d, const CUtensorMap& tmx, const StreamArgs& a, cudaStream_t st) {
+  static bool once = false;
+  if (!once) {
+    MVFB_CUDA(cudaFuncSetAttribute(mvf_stream_fwd_kernel<PASS_APPLY, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    MVFB_CUDA(cudaFuncSetAttribute(mvf_stream_fwd_kernel<PASS_STATS, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    MVFB_CUDA(cudaFuncSetAttribute(mvf_stream_fwd_kernel<PASS_TRAIN, V>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    once = true;
+  }
+  const StreamGeo& g = a.g;
+  const dim3 grid(g.ngroups * g.hsplit * g.P), block(32 * (g.cwarps + 1));
+  const size_t smem = stream_smem(g);
+  if (d->use_hs && d->training) {
+    mvf_stream_fwd_kernel<PASS_STATS, V><<<grid, block, smem, st>>>(tmx, a);
+    count_launch();
+    MVFB_LAUNCH_CHECK();
+    mvf_stream_fwd_kernel<PASS_TRAIN, V><<<grid, block, smem, st>>>(tmx, a);
+  } else {
+    mvf_stream_fwd_kernel<PASS_APPLY, V><<<grid, block, smem, st>>>(tmx, a);
+  }
+  count_launch();
+  MVFB_LAUNCH_CHECK();
+  return MVFB_OK;
 }
 
 }  // namespace
@@ -440,31 +524,14 @@ int mvf_stream_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_s
   StreamArgs a;
   a.g = g;
   a.use_hs = d->use_hs; a.eps = d->eps; a.momentum = d->momentum;
+  static const int debug = getenv("MVFB_STREAM_DEBUG") ? atoi(getenv("MVFB_STREAM_DEBUG")) : 0;
+  a.debug = debug;
   a.wt = wt; a.wh = d->mode != MVFB_MODE_T ? wh : nullptr; a.ww = d->mode == MVFB_MODE_THW ? ww : nullptr;
   a.gamma = gamma; a.beta = beta; a.running_mean = rm; a.running_var = rv;
   a.save_mean = save_mean; a.save_rstd = save_rstd;
   a.partials = (float*)ws;
   a.y = (__nv_bfloat16*)y; a.y_pix = y_stride;
-  static bool once = false;
-  if (!once) {
-    MVFB_CUDA(cudaFuncSetAttribute(mvf_stream_fwd_kernel<PASS_APPLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    MVFB_CUDA(cudaFuncSetAttribute(mvf_stream_fwd_kernel<PASS_STATS>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    MVFB_CUDA(cudaFuncSetAttribute(mvf_stream_fwd_kernel<PASS_TRAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    once = true;
-  }
-  const dim3 grid(g.ngroups * g.hsplit * g.P), block(32 * (g.cwarps + 1));
-  const size_t smem = stream_smem(g);
-  if (d->use_hs && d->training) {
-    mvf_stream_fwd_kernel<PASS_STATS><<<grid, block, smem, st>>>(tmx, a);
-    count_launch();
-    MVFB_LAUNCH_CHECK();
-    mvf_stream_fwd_kernel<PASS_TRAIN><<<grid, block, smem, st>>>(tmx, a);
-  } else {
-    mvf_stream_fwd_kernel<PASS_APPLY><<<grid, block, smem, st>>>(tmx, a);
-  }
-  count_launch();
-  MVFB_LAUNCH_CHECK();
-  return MVFB_OK;
+  return g.V == 8 ? launch_stream<8>(d, tmx, a, st) : launch_stream<4>(d, tmx, a, st);
 }
 
 }  // namespace mvfb
