@@ -119,6 +119,22 @@ int conv1x1_gemm(const mvfb_gemm_desc* d, const void* a0, const void* a1, const 
                  float* colsq, mvfb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * 3x3 / pad 1 / stride 1|2 convolution on NHWC bf16 activations as an implicit GEMM on the tensor cores  --
+ * replaces Bottleneck.conv2 (backbones/resnet.py:163-170, stride per :151-153); with the spatially rotated,
+ * channel-transposed weights it is also the stride-1 input-gradient.
+ *   out[f, ho, wo, n] = sum_{r,s,c} x[f, ho*stride + r - 1, wo*stride + s - 1, c] * w[n, r, s, c]
+ * x: (F, H, W, Cin); w: (Cout, 3, 3, Cin) (= a channels_last torch weight); out: (F, Ho, Wo, Cout); all bf16,
+ * contiguous.  The A operand is gathered by TMA im2col loads (zero fill = padding); the rest is conv1x1_gemm's
+ * kernel, including the optional per-channel (sum, sum of squares) epilogue.  Cin, Cout multiples of 64.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+  int F, H, W, Cin, Cout, stride;
+} mvfb_conv_desc;
+
+int conv3x3_gemm(const mvfb_conv_desc* d, const void* x, const void* w, void* out, float* colsum, float* colsq,
+                 mvfb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
  * BatchNorm2d (+ residual add) (+ ReLU) on NHWC bf16 activations viewed as (M = F*H*W, C) rows  --  replaces
  * norm1+relu, norm2+relu, norm3 / downsample norm + `out += identity` + relu of Bottleneck.forward
  * (backbones/resnet.py:213-242; nn.BatchNorm2d semantics as common/norm.py:66 builds it: eps 1e-5,

@@ -39,6 +39,9 @@ struct GemmArgs {
   int m_tiles, n_tiles;
   float* colsum;                   // [N] or null
   float* colsq;                    // [N] or null
+  // 3x3 convolution as an implicit GEMM (IM2COL kernels): K = 9 * Cin ordered (r, s, c); A tiles are gathered by
+  // TMA im2col loads from the NHWC input, M = F * Ho * Wo output pixels
+  int Cin, Ho, Wo, stride;
 };
 
 template <int BN>
@@ -57,7 +60,7 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int BN>
+template <int BN, bool IM2COL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD, const GemmArgs a) {
@@ -108,12 +111,28 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
         const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+        // IM2COL: first output pixel of the tile -> base input pixel of its filter window (pad 1)
+        int bw = 0, bh = 0, bn = 0, cblocks = 1;
+        if (IM2COL) {
+          const long long m0 = (long long)mt * BM;
+          const int q = (int)(m0 % a.Wo), pq = (int)(m0 / a.Wo);
+          bw = q * a.stride - 1;
+          bh = (pq % a.Ho) * a.stride - 1;
+          bn = pq / a.Ho;
+          cblocks = a.Cin / BK;
+        }
+        int rs = 0, cb = 0;                                    // filter tap (r*3+s) and channel block of this k-block
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sa = stage_base + (size_t)s * C::kStageBytes;
           mbar_arrive_expect_tx(&full[s], C::kStageBytes);
           const int k = kb * BK;
-          tma_load_2d(sa, k < a.K0 ? &tmA0 : &tmA1, &full[s], k, mt * BM);
+          if (IM2COL) {
+            tma_load_im2col_4d(sa, &tmA1, &full[s], cb * BK, bw, bh, bn, (uint16_t)(rs % 3), (uint16_t)(rs / 3));
+            if (++cb == cblocks) { cb = 0; ++rs; }
+          } else {
+            tma_load_2d(sa, k < a.K0 ? &tmA0 : &tmA1, &full[s], k, mt * BM);
+          }
           tma_load_2d(sa + C::kABytes, &tmB, &full[s], k, nt * BN);
           if (++s == C::kStages) { s = 0; ph ^= 1; }
         }
@@ -232,6 +251,25 @@ int make_2d_map(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 }
 
+template <int BN, bool IM2COL>
+int launch_kernel(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmB, const CUtensorMap& tmD,
+                  GemmArgs a, cudaStream_t st) {
+  using C = Cfg<BN>;
+  a.m_tiles = (int)((a.M + BM - 1) / BM);
+  a.n_tiles = a.N / BN;
+  static bool once = false;
+  if (!once) {
+    MVFB_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+    once = true;
+  }
+  int grid = a.m_tiles * a.n_tiles;
+  if (grid > num_sms()) grid = num_sms();
+  gemm_tn_kernel<BN, IM2COL><<<grid, kThreads, C::kSmem, st>>>(tmA0, tmA1, tmB, tmD, a);
+  count_launch();
+  MVFB_LAUNCH_CHECK();
+  return MVFB_OK;
+}
+
 template <int BN>
 int launch(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, void* out, float* colsum,
            float* colsq, cudaStream_t st) {
@@ -249,20 +287,32 @@ int launch(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* 
   if ((rc = make_2d_map(&tmD, out, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldd, 64, BM))) return rc;
   GemmArgs a;
   a.M = d->M; a.N = d->N; a.K = d->K; a.K0 = d->K0;
-  a.m_tiles = (int)((d->M + BM - 1) / BM);
-  a.n_tiles = d->N / BN;
   a.colsum = colsum; a.colsq = colsq;
-  static bool once = false;
-  if (!once) {
-    MVFB_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
-    once = true;
-  }
-  int grid = a.m_tiles * a.n_tiles;
-  if (grid > num_sms()) grid = num_sms();
-  gemm_tn_kernel<BN><<<grid, kThreads, C::kSmem, st>>>(tmA0, tmA1, tmB, tmD, a);
-  count_launch();
-  MVFB_LAUNCH_CHECK();
-  return MVFB_OK;
+  a.Cin = a.Ho = a.Wo = a.stride = 0;
+  return launch_kernel<BN, false>(tmA0, tmA1, tmB, tmD, a, st);
+}
+
+// 3x3 / pad 1 convolution: A gathered by TMA im2col from x (F, H, W, Cin); B = weights (Cout, 3, 3, Cin)
+template <int BN>
+int launch_conv3x3(const mvfb_conv_desc* d, const void* x, const void* w, void* out, float* colsum, float* colsq,
+                   cudaStream_t st) {
+  const int Ho = (d->H - 1) / d->stride + 1, Wo = (d->W - 1) / d->stride + 1;
+  CUtensorMap tmA, tmB, tmD;
+  const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->F};
+  const uint64_t strides[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
+  const int lower[2] = {-1, -1}, upper[2] = {-1, -1};          // pad 1; upper = pad - (kernel - 1)
+  const uint32_t estr[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
+  int rc = encode_tmap_im2col(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, lower, upper, BK, BM, estr,
+                              CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc) return rc;
+  const long long M = (long long)d->F * Ho * Wo;
+  if ((rc = make_2d_map(&tmB, w, (uint64_t)9 * d->Cin, (uint64_t)d->Cout, (uint64_t)9 * d->Cin, BK, BN))) return rc;
+  if ((rc = make_2d_map(&tmD, out, (uint64_t)d->Cout, (uint64_t)M, (uint64_t)d->Cout, 64, BM))) return rc;
+  GemmArgs a;
+  a.M = M; a.N = d->Cout; a.K = 9 * d->Cin; a.K0 = 0;
+  a.colsum = colsum; a.colsq = colsq;
+  a.Cin = d->Cin; a.Ho = Ho; a.Wo = Wo; a.stride = d->stride;
+  return launch_kernel<BN, true>(tmA, tmA, tmB, tmD, a, st);
 }
 
 }  // namespace
@@ -288,4 +338,20 @@ extern "C" int conv1x1_gemm(const mvfb_gemm_desc* d, const void* a0, const void*
   if (d->N % 256 == 0) return launch<256>(d, a0, a1, b, out, colsum, colsq, st);
   if (d->N % 128 == 0) return launch<128>(d, a0, a1, b, out, colsum, colsq, st);
   return launch<64>(d, a0, a1, b, out, colsum, colsq, st);
+}
+
+extern "C" int conv3x3_gemm(const mvfb_conv_desc* d, const void* x, const void* w, void* out, float* colsum,
+                            float* colsq, mvfb_stream_t stream) {
+  MVFB_CHECK(d && x && w && out, MVFB_ERR_ARG, "null descriptor / operand");
+  MVFB_CHECK(d->F > 0 && d->H > 0 && d->W > 0 && (d->stride == 1 || d->stride == 2), MVFB_ERR_ARG,
+             "bad conv shape F=%d H=%d W=%d stride=%d", d->F, d->H, d->W, d->stride);
+  MVFB_CHECK(d->Cin % BK == 0 && d->Cout % 64 == 0, MVFB_ERR_UNSUPPORTED, "Cin=%d and Cout=%d must be multiples of 64",
+             d->Cin, d->Cout);
+  MVFB_CHECK((colsum == nullptr) == (colsq == nullptr), MVFB_ERR_ARG, "colsum and colsq go together");
+  MVFB_CHECK(!((uintptr_t)x & 15) && !((uintptr_t)w & 15) && !((uintptr_t)out & 15), MVFB_ERR_UNSUPPORTED,
+             "operands must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->Cout % 256 == 0) return launch_conv3x3<256>(d, x, w, out, colsum, colsq, st);
+  if (d->Cout % 128 == 0) return launch_conv3x3<128>(d, x, w, out, colsum, colsq, st);
+  return launch_conv3x3<64>(d, x, w, out, colsum, colsq, st);
 }

@@ -25,6 +25,11 @@ class GemmDesc(C.Structure):
                 ("lda0", C.c_longlong), ("lda1", C.c_longlong), ("ldb", C.c_longlong), ("ldd", C.c_longlong)]
 
 
+class ConvDesc(C.Structure):
+    """mvfb_conv_desc (include/mvf_b200.h)."""
+    _fields_ = [(n, C.c_int) for n in ("F", "H", "W", "Cin", "Cout", "stride")]
+
+
 class BnDesc(C.Structure):
     """mvfb_bn_desc (include/mvf_b200.h)."""
     _fields_ = [("M", C.c_longlong), ("C", C.c_int), ("relu", C.c_int), ("training", C.c_int),
@@ -41,6 +46,8 @@ def _L():
     if not _declared:
         L.conv1x1_gemm.restype = C.c_int
         L.conv1x1_gemm.argtypes = [C.POINTER(GemmDesc), _VP, _VP, _VP, _VP, _VP, _VP, _VP]
+        L.conv3x3_gemm.restype = C.c_int
+        L.conv3x3_gemm.argtypes = [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, _VP]
         L.bn_stats.restype = C.c_int
         L.bn_stats.argtypes = [C.POINTER(BnDesc), _VP, _LL, _VP, _VP]
         L.bn_apply.restype = C.c_int
@@ -50,6 +57,10 @@ def _L():
                              _VP, _VP, _VP]
         _declared = True
     return L
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 def enabled() -> bool:
@@ -188,6 +199,77 @@ def mvf_conv1x1(x, weight, wt, wh, ww, gamma, beta, running_mean, running_var, c
     return _MVFConv1x1.apply(x, weight, wt, wh, ww, gamma, beta, running_mean, running_var, cfg, stats)
 
 
+# ------------------------------------------------------------------------------------------------ 3x3 convolution
+def conv3x3_enabled() -> bool:
+    """MVFB_CONV3X3=0 routes the 3x3 convolutions back through torch / cuDNN (A/B measurements only)."""
+    return os.environ.get("MVFB_CONV3X3", "1") != "0"
+
+
+def conv3x3_eligible(x, conv):
+    return (conv3x3_enabled() and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4
+            and type(conv) is torch.nn.Conv2d and conv.kernel_size == (3, 3) and conv.padding == (1, 1)
+            and conv.dilation == (1, 1) and conv.groups == 1 and conv.bias is None and conv.stride in ((1, 1), (2, 2))
+            and conv.in_channels % 64 == 0 and conv.out_channels % 64 == 0 and x.shape[1] == conv.in_channels
+            and x.is_contiguous(memory_format=torch.channels_last))
+
+
+def conv3x3_raw(x, w_krsc, stride, stats=False):
+    """x: (F, Cin, H, W) bf16 channels_last; w_krsc: (Cout, 3, 3, Cin) bf16 contiguous -> ((F, Cout, Ho, Wo), sums)."""
+    L = _L()
+    f, cin, h, w = x.shape
+    cout = w_krsc.shape[0]
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    d = ConvDesc()
+    d.F, d.H, d.W, d.Cin, d.Cout, d.stride = f, h, w, cin, cout, stride
+    out = torch.empty((f, ho, wo, cout), dtype=torch.bfloat16, device=x.device)
+    sums = torch.zeros((2, cout), dtype=torch.float32, device=x.device) if stats else None
+    rc = L.conv3x3_gemm(C.byref(d), ptr(x), ptr(w_krsc), ptr(out), ptr(sums[0]) if stats else None,
+                        ptr(sums[1]) if stats else None, _stream())
+    _lib.check(rc, "conv3x3_gemm")
+    return out.permute(0, 3, 1, 2), sums
+
+
+class _Conv3x3(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, weight, stride, stats):
+        wb = weight.detach().to(torch.bfloat16)
+        y, sums = conv3x3_raw(x, wb.permute(0, 2, 3, 1).contiguous(), stride, stats)
+        ctx.stride = stride
+        ctx.save_for_backward(x, wb)
+        if not stats:
+            return y
+        ctx.mark_non_differentiable(sums)
+        return y, sums
+
+    @staticmethod
+    def backward(ctx, g, *unused):
+        x, wb = ctx.saved_tensors
+        st = ctx.stride
+        g = g.contiguous(memory_format=torch.channels_last)
+        dx = dw = None
+        need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
+        if need_dx and st == 1:
+            # stride-1 input gradient = the same convolution with spatially rotated, channel-transposed weights
+            w_rot = wb.flip(2, 3).permute(1, 2, 3, 0).contiguous()          # (Cin, 3, 3, Cout)
+            dx, _ = conv3x3_raw(g, w_rot, 1)
+            need_dx = False
+        if need_dx or need_dw:
+            wcl = wb.contiguous(memory_format=torch.channels_last)
+            r = torch.ops.aten.convolution_backward(g, x, wcl, None, [st, st], [1, 1], [1, 1], False, [0, 0], 1,
+                                                    [need_dx, need_dw, False])
+            if need_dx:
+                dx = r[0]
+            if need_dw:
+                dw = r[1].float()
+        return dx, dw, None, None
+
+
+def conv3x3(x, weight, stride=1, stats=False):
+    """3x3 / pad 1 bias-free convolution of a bf16 channels_last tensor: forward and stride-1 input-gradient on the
+    tcgen05 implicit GEMM (TMA im2col); weight-gradient and the stride-2 input-gradient are library calls."""
+    return _Conv3x3.apply(x, weight, stride, stats)
+
+
 # ------------------------------------------------------------------------------------------------ BatchNorm
 def bn_enabled() -> bool:
     """MVFB_BN=0 routes BatchNorm / ReLU / residual back through torch (A/B measurements only)."""
@@ -198,10 +280,6 @@ def bn_eligible(x, bn):
     return (bn_enabled() and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and type(bn) is torch.nn.BatchNorm2d
             and bn.affine and x.shape[1] % 8 == 0 and x.shape[1] <= 2048
             and x.is_contiguous(memory_format=torch.channels_last))
-
-
-def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
 class _BNAct(torch.autograd.Function):

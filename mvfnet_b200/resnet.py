@@ -45,6 +45,16 @@ def _conv1x1(conv, x, want_stats=False):
     return conv(x), None
 
 
+def _conv3x3(conv, x, want_stats=False):
+    """Bottleneck.conv2 on the tcgen05 implicit GEMM when eligible (bf16 channels_last), else the module itself."""
+    from . import ops
+    if ops.conv3x3_eligible(x, conv):
+        if want_stats:
+            return ops.conv3x3(x, conv.weight, conv.stride[0], True)
+        return ops.conv3x3(x, conv.weight, conv.stride[0]), None
+    return conv(x), None
+
+
 def _bn_act(bn, x, relu, residual=None, sums=None, relu_module=None):
     """BatchNorm2d (+ residual) (+ ReLU): one fused kernel pair when eligible, the torch modules otherwise."""
     from . import ops
@@ -95,7 +105,8 @@ class Bottleneck(nn.Module):
         identity = x
         out, sums = _conv1x1(self.conv1, x, fuse)
         out = _bn_act(self.norm1, out, True, sums=sums, relu_module=self.relu)
-        out = _bn_act(self.norm2, self.conv2(out), True, relu_module=self.relu)
+        out, sums = _conv3x3(self.conv2, out, fuse)
+        out = _bn_act(self.norm2, out, True, sums=sums, relu_module=self.relu)
         out, sums = _conv1x1(self.conv3, out, fuse)
         if self.downsample is not None:
             ds, dsums = _conv1x1(self.downsample[0], x, fuse)

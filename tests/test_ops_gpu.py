@@ -159,3 +159,36 @@ def test_fused_bottleneck_vs_torch_fp32(inpl, planes, hw, stride, mvf, monkeypat
     for (k, b), (_, c) in zip(blk.named_buffers(), ref.named_buffers()):
         if "running" in k:
             assert rel(b.float(), c.float()) < 2e-2, k
+
+
+@pytest.mark.parametrize("F,Cin,Cout,H,stride", [(4, 64, 64, 56, 1), (8, 128, 128, 28, 1), (8, 256, 256, 14, 1), (16, 512, 512, 7, 1),
+                                                 (4, 128, 128, 56, 2), (8, 256, 256, 28, 2), (8, 512, 512, 14, 2), (3, 64, 192, 9, 1)])
+def test_conv3x3_implicit_gemm(F, Cin, Cout, H, stride):
+    """TMA-im2col implicit GEMM vs torch conv2d in fp32 on the same bf16-rounded operands; forward, fused statistics,
+    and the stride-1 input gradient (rotated weights through the same kernel)."""
+    from mvfnet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(F + Cin + H)
+    x = torch.randn(F, Cin, H, H, device="cuda", generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (3 * Cin ** 0.5)).bfloat16()
+    y, sums = ops.conv3x3_raw(x, w.permute(0, 2, 3, 1).contiguous(), stride, stats=True)
+    ref = torch.nn.functional.conv2d(x.float(), w.float(), None, stride, 1)
+    assert y.shape == ref.shape
+    err = rel(y, ref)
+    if err >= 1e-2:      # diagnose an off-by-one in the im2col base coordinates before failing
+        for dh in (-1, 0, 1):
+            for dw in (-1, 0, 1):
+                shifted = torch.roll(ref, shifts=(dh, dw), dims=(2, 3))
+                print("shift", dh, dw, rel(y[:, :, 2:-2, 2:-2], shifted[:, :, 2:-2, 2:-2]))
+    assert err < 1e-2
+    assert rel(sums[0], y.float().sum((0, 2, 3))) < 1e-3 or float((sums[0] - y.float().sum((0, 2, 3))).abs().max()) < 1e-2 * float(y.float().abs().sum((0, 2, 3)).max())
+    assert rel(sums[1], (y.float() ** 2).sum((0, 2, 3))) < 1e-3
+    # autograd: dx (ours for stride 1, library for stride 2) and dw vs torch fp32
+    xr = x.float().requires_grad_(True)
+    wr = w.float().requires_grad_(True)
+    gy = torch.randn_like(ref)
+    torch.nn.functional.conv2d(xr, wr, None, stride, 1).backward(gy)
+    xo = x.clone().requires_grad_(True)
+    wo = w.float().clone().requires_grad_(True)
+    ops.conv3x3(xo, wo, stride).backward(gy.bfloat16().contiguous(memory_format=torch.channels_last))
+    assert rel(xo.grad, xr.grad) < 2e-2
+    assert rel(wo.grad, wr.grad) < 2e-2
