@@ -161,12 +161,13 @@ def test_fused_bottleneck_vs_torch_fp32(inpl, planes, hw, stride, mvf, monkeypat
             assert rel(b.float(), c.float()) < 2e-2, k
 
 
-@pytest.mark.parametrize("F,Cin,Cout,H,stride", [(4, 64, 64, 56, 1), (8, 128, 128, 28, 1), (8, 256, 256, 14, 1), (16, 512, 512, 7, 1),
-                                                 (4, 128, 128, 56, 2), (8, 256, 256, 28, 2), (8, 512, 512, 14, 2), (3, 64, 192, 9, 1)])
+@pytest.mark.parametrize("F,Cin,Cout,H,stride", [(2, 64, 64, 56, 1), (4, 128, 128, 28, 1), (8, 256, 256, 14, 1), (16, 512, 512, 7, 1),
+                                                 (2, 128, 128, 56, 2), (4, 256, 256, 28, 2), (4, 512, 512, 14, 2), (3, 64, 192, 9, 1)])
 def test_conv3x3_implicit_gemm(F, Cin, Cout, H, stride):
     """TMA-im2col implicit GEMM vs torch conv2d in fp32 on the same bf16-rounded operands; forward, fused statistics,
     and the stride-1 input gradient (rotated weights through the same kernel)."""
     from mvfnet_b200 import ops
+    torch.backends.cudnn.allow_tf32 = True       # the fp32 reference conv is only a yard-stick at 1e-2; keep it fast
     g = torch.Generator(device="cuda").manual_seed(F + Cin + H)
     x = torch.randn(F, Cin, H, H, device="cuda", generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
     w = (torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (3 * Cin ** 0.5)).bfloat16()
