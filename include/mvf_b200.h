@@ -118,6 +118,13 @@ typedef struct {
 int conv1x1_gemm(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, void* out, float* colsum,
                  float* colsq, mvfb_stream_t stream);
 
+/* Weight gradient of the same layer: dw[n, k] = sum_m g[m*ldb + n] * X[m, k], X = [x0[:, :K0] | x1[:, K0:]] as above
+ * (M = pixels, N = Cout, K = Cin; lda0 / lda1 / ldb = leading dimensions of x0 / x1 / g; dw is fp32 (N, ldd) and is
+ * zeroed by the call, then accumulated with fp32 atomics over split-K partitions of the pixel axis).  Both MMA
+ * operands are MN-major views of the NHWC tensors: no transposed copies are made. */
+int conv1x1_wgrad(const mvfb_gemm_desc* d, const void* g, const void* x0, const void* x1, float* dw,
+                  mvfb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * 3x3 / pad 1 / stride 1|2 convolution on NHWC bf16 activations as an implicit GEMM on the tensor cores  --
  * replaces Bottleneck.conv2 (backbones/resnet.py:163-170, stride per :151-153); with the spatially rotated,

@@ -46,6 +46,8 @@ def _L():
     if not _declared:
         L.conv1x1_gemm.restype = C.c_int
         L.conv1x1_gemm.argtypes = [C.POINTER(GemmDesc), _VP, _VP, _VP, _VP, _VP, _VP, _VP]
+        L.conv1x1_wgrad.restype = C.c_int
+        L.conv1x1_wgrad.argtypes = [C.POINTER(GemmDesc), _VP, _VP, _VP, _VP, _VP]
         L.conv3x3_gemm.restype = C.c_int
         L.conv3x3_gemm.argtypes = [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, _VP]
         L.bn_stats.restype = C.c_int
@@ -102,6 +104,31 @@ def gemm_tn(a1, b, a0=None, k0=0, stats=False, out=None):
     return out, colsum, colsq
 
 
+def wgrad_enabled() -> bool:
+    """MVFB_WGRAD=0 computes 1x1 weight gradients with torch.matmul (A/B measurements only)."""
+    return os.environ.get("MVFB_WGRAD", "1") != "0"
+
+
+def gemm_wgrad(g2, x1, x0=None, k0=0):
+    """dW[n, k] = sum_m g2[m, n] X[m, k] with X = [x0[:, :k0] | x1[:, k0:]] -> fp32 (N, K).  bf16 row-major inputs."""
+    if not wgrad_enabled():
+        gt = g2.t()
+        if x0 is None:
+            return torch.matmul(gt, x1).float()
+        return torch.cat([torch.matmul(gt, x0), torch.matmul(gt, x1[:, k0:])], dim=1).float()
+    L = _L()
+    m, n = g2.shape
+    k = x1.shape[1]
+    dw = torch.empty((n, k), dtype=torch.float32, device=g2.device)
+    d = GemmDesc()
+    d.M, d.N, d.K, d.K0 = m, n, k, k0
+    d.lda1, d.ldb, d.ldd = x1.stride(0), g2.stride(0), k
+    d.lda0 = x0.stride(0) if x0 is not None else 0
+    rc = L.conv1x1_wgrad(C.byref(d), ptr(g2), ptr(x0), ptr(x1), ptr(dw), _stream())
+    _lib.check(rc, "conv1x1_wgrad")
+    return dw
+
+
 def _nhwc_from_rows(rows, f, h, w):
     return rows.view(f, h, w, rows.shape[1]).permute(0, 3, 1, 2)
 
@@ -131,7 +158,7 @@ class _Conv1x1(torch.autograd.Function):
             dx2, _, _ = gemm_tn(g2, wb.t().contiguous())               # dX = dY W  ==  TN GEMM against W^T
             dx = _nhwc_from_rows(dx2, f, h, w)
         if ctx.needs_input_grad[1]:
-            dw = torch.matmul(g2.t(), _rows(x)).float().view(wb.shape[0], cin, 1, 1)
+            dw = gemm_wgrad(g2, _rows(x)).view(wb.shape[0], cin, 1, 1)
         return dx, dw, None
 
 
@@ -174,9 +201,7 @@ class _MVFConv1x1(torch.autograd.Function):
         dxp, _, _ = gemm_tn(g2, wb.t().contiguous())
         dw = None
         if ctx.needs_input_grad[1]:
-            gt = g2.t()
-            dw = torch.cat([torch.matmul(gt, _rows(slab)), torch.matmul(gt, _rows(xk)[:, cs:])], dim=1)
-            dw = dw.float().view(wb.shape[0], c, 1, 1)
+            dw = gemm_wgrad(g2, _rows(xk), x0=_rows(slab), k0=cs).view(wb.shape[0], c, 1, 1)
         dx = _nhwc_from_rows(dxp, f, h, w)
         d = _mvf._make_desc(xk, layout, cfg)
         dev = xk.device

@@ -193,3 +193,19 @@ def test_conv3x3_implicit_gemm(F, Cin, Cout, H, stride):
     ops.conv3x3(xo, wo, stride).backward(gy.bfloat16().contiguous(memory_format=torch.channels_last))
     assert rel(xo.grad, xr.grad) < 2e-2
     assert rel(wo.grad, wr.grad) < 2e-2
+
+
+@pytest.mark.parametrize("M,N,K,K0", [(4704, 512, 2048, 0), (50176, 256, 1024, 128), (100352, 64, 256, 0), (12544, 2048, 512, 0),
+                                      (1000, 64, 64, 0), (6272, 256, 512, 64), (777, 128, 192, 0)])
+def test_wgrad_mn_major_gemm(M, N, K, K0):
+    """dW = dY^T X on the tensor cores with MN-major operands and split-K atomics vs an fp32 matmul."""
+    from mvfnet_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    dy = torch.randn(M, N, device="cuda", generator=g).bfloat16()
+    x1 = torch.randn(M, K, device="cuda", generator=g).bfloat16()
+    x0 = torch.randn(M, K0, device="cuda", generator=g).bfloat16() if K0 else None
+    dw = ops.gemm_wgrad(dy, x1, x0=x0, k0=K0)
+    xcat = x1.float() if x0 is None else torch.cat([x0.float(), x1[:, K0:].float()], dim=1)
+    ref = dy.float().t() @ xcat
+    assert dw.dtype == torch.float32 and dw.shape == ref.shape
+    assert rel(dw, ref) < 2e-3
