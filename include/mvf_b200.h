@@ -141,6 +141,11 @@ typedef struct {
 int conv3x3_gemm(const mvfb_conv_desc* d, const void* x, const void* w, void* out, float* colsum, float* colsq,
                  mvfb_stream_t stream);
 
+/* Its weight gradient: dw[n, r, s, c] = sum_{f,ho,wo} g[f, ho, wo, n] * x[f, ho*stride + r - 1, wo*stride + s - 1, c]
+ * (g bf16 (F, Ho, Wo, Cout); dw fp32 (Cout, 3, 3, Cin), zeroed by the call; MN-major MMA operands, the x operand
+ * gathered by TMA im2col, split-K fp32 atomics over the pixel axis). */
+int conv3x3_wgrad(const mvfb_conv_desc* d, const void* g, const void* x, float* dw, mvfb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * BatchNorm2d (+ residual add) (+ ReLU) on NHWC bf16 activations viewed as (M = F*H*W, C) rows  --  replaces
  * norm1+relu, norm2+relu, norm3 / downsample norm + `out += identity` + relu of Bottleneck.forward

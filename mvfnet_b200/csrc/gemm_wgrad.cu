@@ -32,10 +32,11 @@ constexpr int kThreads = 192;
 struct WArgs {
   long long M;                     // pixels
   int N, K, K0;                    // Cout, Cin, Cin taken from X0
-  int n_tiles, k_tiles, splits;    // tiles along Cout, along Cin; k-range count
+  int n_tiles, k_tiles, splits;    // tiles along Cout, along Cin (x 9 filter taps for IM2COL); k-range count
   int pblocks;                     // ceil(M / 64)
   float* dw;
   long long lddw;
+  int Ho, Wo, stride;              // IM2COL (3x3 / pad 1): output geometry; dw is (Cout, 3, 3, Cin)
 };
 
 template <int BN>
@@ -57,7 +58,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN>
+template <int BN, bool IM2COL>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX0,
                   const __grid_constant__ CUtensorMap tmX1, const WArgs a) {
@@ -74,6 +75,9 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   // work item -> (cout tile, cin tile, pixel range)
   const int tile = blockIdx.x / a.splits, split = blockIdx.x - tile * a.splits;
   const int nt = tile / a.k_tiles, kt = tile - nt * a.k_tiles;
+  // IM2COL: kt enumerates (filter tap rs, channel tile ct); the tap's input pixels are gathered by TMA im2col
+  const int ctiles = a.K / BN;
+  const int rs = IM2COL ? kt / ctiles : 0, ct = IM2COL ? kt - rs * ctiles : kt;
   const int per = (a.pblocks + a.splits - 1) / a.splits;
   const int pb0 = split * per;
   int pb1 = pb0 + per;
@@ -111,10 +115,19 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         const int p = (pb0 + i) * BKP;
 #pragma unroll
         for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BKP * 128), &tmG, &full[s], nt * BM + j * 64, p);
+        if (IM2COL) {
+          const int q = p % a.Wo, pq = p / a.Wo;                // first output pixel of the block -> window origin
+          const int bw = q * a.stride - 1, bh = (pq % a.Ho) * a.stride - 1, bn = pq / a.Ho;
 #pragma unroll
-        for (int j = 0; j < BN / 64; ++j) {
-          const int c = kt * BN + j * 64;
-          tma_load_2d(sa + C::kABytes + j * (BKP * 128), c < a.K0 ? &tmX0 : &tmX1, &full[s], c, p);
+          for (int j = 0; j < BN / 64; ++j)
+            tma_load_im2col_4d(sa + C::kABytes + j * (BKP * 128), &tmX1, &full[s], ct * BN + j * 64, bw, bh, bn,
+                               (uint16_t)(rs % 3), (uint16_t)(rs / 3));
+        } else {
+#pragma unroll
+          for (int j = 0; j < BN / 64; ++j) {
+            const int c = ct * BN + j * 64;
+            tma_load_2d(sa + C::kABytes + j * (BKP * 128), c < a.K0 ? &tmX0 : &tmX1, &full[s], c, p);
+          }
         }
         if (++s == C::kStages) { s = 0; ph ^= 1; }
       }
@@ -144,7 +157,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     mbar_wait(done, 0);
     tc_fence_after();
     const uint32_t taddr = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
-    float* dst = a.dw + (size_t)row * a.lddw + (size_t)kt * BN;
+    float* dst = a.dw + (size_t)row * a.lddw + (size_t)rs * a.K + (size_t)ct * BN;
 #pragma unroll 1
     for (int c0 = 0; c0 < BN; c0 += 32) {
       uint32_t v[32];
@@ -175,9 +188,32 @@ int map_64x64(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, u
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 }
 
+template <int BN, bool IM2COL>
+int launch_wgrad_kernel(const CUtensorMap& tmG, const CUtensorMap& tmX0, const CUtensorMap& tmX1, WArgs a, size_t dw_elems,
+                        cudaStream_t st) {
+  using C = WCfg<BN>;
+  a.n_tiles = (a.N + BM - 1) / BM;
+  a.k_tiles = (a.K / BN) * (IM2COL ? 9 : 1);
+  a.pblocks = (int)((a.M + BKP - 1) / BKP);
+  const int tiles = a.n_tiles * a.k_tiles;
+  int splits = (2 * num_sms() + tiles - 1) / tiles;            // ~2 CTAs worth of work items per SM
+  if (splits > a.pblocks) splits = a.pblocks;
+  if (splits < 1) splits = 1;
+  a.splits = splits;
+  static bool once = false;
+  if (!once) {
+    MVFB_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel<BN, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+    once = true;
+  }
+  MVFB_CUDA(cudaMemsetAsync(a.dw, 0, sizeof(float) * dw_elems, st));
+  gemm_wgrad_kernel<BN, IM2COL><<<tiles * splits, kThreads, C::kSmem, st>>>(tmG, tmX0, tmX1, a);
+  count_launch();
+  MVFB_LAUNCH_CHECK();
+  return MVFB_OK;
+}
+
 template <int BN>
 int launch_wgrad(const mvfb_gemm_desc* d, const void* g, const void* x0, const void* x1, float* dw, cudaStream_t st) {
-  using C = WCfg<BN>;
   CUtensorMap tmG, tmX0, tmX1;
   int rc;
   if ((rc = map_64x64(&tmG, g, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldb))) return rc;
@@ -189,25 +225,31 @@ int launch_wgrad(const mvfb_gemm_desc* d, const void* g, const void* x0, const v
   }
   WArgs a;
   a.M = d->M; a.N = d->N; a.K = d->K; a.K0 = d->K0;
-  a.n_tiles = (d->N + BM - 1) / BM;
-  a.k_tiles = d->K / BN;
-  a.pblocks = (int)((d->M + BKP - 1) / BKP);
-  const int tiles = a.n_tiles * a.k_tiles;
-  int splits = (2 * num_sms() + tiles - 1) / tiles;            // ~2 CTAs worth of work items per SM
-  if (splits > a.pblocks) splits = a.pblocks;
-  if (splits < 1) splits = 1;
-  a.splits = splits;
   a.dw = dw; a.lddw = d->ldd;
-  static bool once = false;
-  if (!once) {
-    MVFB_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
-    once = true;
-  }
-  MVFB_CUDA(cudaMemsetAsync(dw, 0, sizeof(float) * (size_t)d->N * d->ldd, st));
-  gemm_wgrad_kernel<BN><<<tiles * splits, kThreads, C::kSmem, st>>>(tmG, tmX0, tmX1, a);
-  count_launch();
-  MVFB_LAUNCH_CHECK();
-  return MVFB_OK;
+  a.Ho = a.Wo = a.stride = 0;
+  return launch_wgrad_kernel<BN, false>(tmG, tmX0, tmX1, a, (size_t)d->N * d->ldd, st);
+}
+
+// 3x3 / pad 1 weight gradient: dw[n, r, s, c] = sum_p g[p, n] * x[window(p) + (r, s), c]
+template <int BN>
+int launch_wgrad3x3(const mvfb_conv_desc* d, const void* g, const void* x, float* dw, cudaStream_t st) {
+  const int Ho = (d->H - 1) / d->stride + 1, Wo = (d->W - 1) / d->stride + 1;
+  const long long M = (long long)d->F * Ho * Wo;
+  CUtensorMap tmG, tmX;
+  int rc;
+  if ((rc = map_64x64(&tmG, g, (uint64_t)d->Cout, (uint64_t)M, (uint64_t)d->Cout))) return rc;
+  const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->F};
+  const uint64_t strides[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
+  const int lower[2] = {-1, -1}, upper[2] = {-1, -1};
+  const uint32_t estr[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
+  if ((rc = encode_tmap_im2col(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, lower, upper, 64, BKP, estr,
+                               CU_TENSOR_MAP_SWIZZLE_128B)))
+    return rc;
+  WArgs a;
+  a.M = M; a.N = d->Cout; a.K = d->Cin; a.K0 = 0;
+  a.dw = dw; a.lddw = 9LL * d->Cin;
+  a.Ho = Ho; a.Wo = Wo; a.stride = d->stride;
+  return launch_wgrad_kernel<BN, true>(tmG, tmX, tmX, a, (size_t)d->Cout * 9 * d->Cin, st);
 }
 
 }  // namespace
@@ -233,4 +275,19 @@ extern "C" int conv1x1_wgrad(const mvfb_gemm_desc* d, const void* g, const void*
   if (d->K % 256 == 0) return launch_wgrad<256>(d, g, x0, x1, dw, st);
   if (d->K % 128 == 0) return launch_wgrad<128>(d, g, x0, x1, dw, st);
   return launch_wgrad<64>(d, g, x0, x1, dw, st);
+}
+
+// g: (F, Ho, Wo, Cout) bf16; x: (F, H, W, Cin) bf16; dw: (Cout, 3, 3, Cin) fp32, zeroed by the call.
+extern "C" int conv3x3_wgrad(const mvfb_conv_desc* d, const void* g, const void* x, float* dw, mvfb_stream_t stream) {
+  MVFB_CHECK(d && g && x && dw, MVFB_ERR_ARG, "null descriptor / operand");
+  MVFB_CHECK(d->F > 0 && d->H > 0 && d->W > 0 && (d->stride == 1 || d->stride == 2), MVFB_ERR_ARG,
+             "bad conv shape F=%d H=%d W=%d stride=%d", d->F, d->H, d->W, d->stride);
+  MVFB_CHECK(d->Cin % 64 == 0 && d->Cout % 64 == 0, MVFB_ERR_UNSUPPORTED, "Cin=%d and Cout=%d must be multiples of 64",
+             d->Cin, d->Cout);
+  MVFB_CHECK(!((uintptr_t)g & 15) && !((uintptr_t)x & 15) && !((uintptr_t)dw & 15), MVFB_ERR_UNSUPPORTED,
+             "operands must be 16-byte aligned");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->Cin % 256 == 0) return launch_wgrad3x3<256>(d, g, x, dw, st);
+  if (d->Cin % 128 == 0) return launch_wgrad3x3<128>(d, g, x, dw, st);
+  return launch_wgrad3x3<64>(d, g, x, dw, st);
 }

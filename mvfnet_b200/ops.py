@@ -50,6 +50,8 @@ def _L():
         L.conv1x1_wgrad.argtypes = [C.POINTER(GemmDesc), _VP, _VP, _VP, _VP, _VP]
         L.conv3x3_gemm.restype = C.c_int
         L.conv3x3_gemm.argtypes = [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, _VP]
+        L.conv3x3_wgrad.restype = C.c_int
+        L.conv3x3_wgrad.argtypes = [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP]
         L.bn_stats.restype = C.c_int
         L.bn_stats.argtypes = [C.POINTER(BnDesc), _VP, _LL, _VP, _VP]
         L.bn_apply.restype = C.c_int
@@ -278,6 +280,14 @@ class _Conv3x3(torch.autograd.Function):
             w_rot = wb.flip(2, 3).permute(1, 2, 3, 0).contiguous()          # (Cin, 3, 3, Cout)
             dx, _ = conv3x3_raw(g, w_rot, 1)
             need_dx = False
+        if need_dw and wgrad_enabled():
+            f, cin, h, w = x.shape
+            d = ConvDesc()
+            d.F, d.H, d.W, d.Cin, d.Cout, d.stride = f, h, w, cin, wb.shape[0], st
+            dwk = torch.empty((wb.shape[0], 3, 3, cin), dtype=torch.float32, device=x.device)
+            _lib.check(_L().conv3x3_wgrad(C.byref(d), ptr(g), ptr(x), ptr(dwk), _stream()), "conv3x3_wgrad")
+            dw = dwk.permute(0, 3, 1, 2)                                  # (Cout, Cin, 3, 3) view of the KRSC buffer
+            need_dw = False
         if need_dx or need_dw:
             wcl = wb.contiguous(memory_format=torch.channels_last)
             r = torch.ops.aten.convolution_backward(g, x, wcl, None, [st, st], [1, 1], [1, 1], False, [0, 0], 1,
