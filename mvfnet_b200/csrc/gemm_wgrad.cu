@@ -72,8 +72,10 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // work item -> (cout tile, cin tile, pixel range)
-  const int tile = blockIdx.x / a.splits, split = blockIdx.x - tile * a.splits;
+  // work item -> (cout tile, cin tile, pixel range).  Tiles vary fastest so that co-resident CTAs work on the SAME
+  // pixel range: the dY / X blocks they share (all 9 filter taps, all channel tiles) are then served by L2.
+  const int ntile_all = a.n_tiles * a.k_tiles;
+  const int split = blockIdx.x / ntile_all, tile = blockIdx.x - split * ntile_all;
   const int nt = tile / a.k_tiles, kt = tile - nt * a.k_tiles;
   // IM2COL: kt enumerates (filter tap rs, channel tile ct); the tap's input pixels are gathered by TMA im2col
   const int ctiles = a.K / BN;

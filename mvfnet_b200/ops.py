@@ -280,7 +280,9 @@ class _Conv3x3(torch.autograd.Function):
             w_rot = wb.flip(2, 3).permute(1, 2, 3, 0).contiguous()          # (Cin, 3, 3, Cout)
             dx, _ = conv3x3_raw(g, w_rot, 1)
             need_dx = False
-        if need_dw and wgrad_enabled():
+        # own 3x3 wgrad where it is within ~1.2x of cuDNN (Cin >= 256: layer3/4); the 9-tap re-read of dY makes it
+        # 1.5-3.7x slower on the 56x56 / 28x28 layers (tools/wgrad_probe.py), which stay on the library this round
+        if need_dw and wgrad_enabled() and (x.shape[1] >= 256 or os.environ.get("MVFB_WGRAD3X3") == "all"):
             f, cin, h, w = x.shape
             d = ConvDesc()
             d.F, d.H, d.W, d.Cin, d.Cout, d.stride = f, h, w, cin, wb.shape[0], st
