@@ -159,6 +159,8 @@ int conv3x3_wgrad(const mvfb_conv_desc* d, const void* g, const void* x, float* 
  *   bn_bwd   : g = dL/dy.  g' = g * (y > 0) when relu;  dbeta = sum g', dgamma = sum g' xhat,
  *              dx = gamma rstd (g' - dbeta/M - xhat dgamma/M)  (training)  or  gamma rstd g'  (eval);
  *              dres (optional) = g' -- the gradient of the residual input.  `sums` is [2][C] scratch.
+ *   relu_mask (optional, M*C/8 bytes): bn_apply records 1 bit per element (y > 0), byte index m*(C/8) + c/8, bit c%8;
+ *              bn_bwd then reads that instead of y (16x less traffic for the mask).
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   long long M;       /* rows = F*H*W                          */
@@ -174,10 +176,11 @@ int copy_cols(const void* x, long long ldx, void* y, long long ldy, long long M,
 int bn_stats(const mvfb_bn_desc* d, const void* x, long long ldx, float* sums, mvfb_stream_t stream);
 int bn_apply(const mvfb_bn_desc* d, const void* x, long long ldx, const void* residual, long long ldr, void* y,
              long long ldy, const float* sums, const float* gamma, const float* beta, float* running_mean,
-             float* running_var, float* save_mean, float* save_rstd, mvfb_stream_t stream);
+             float* running_var, float* save_mean, float* save_rstd, unsigned char* relu_mask, mvfb_stream_t stream);
 int bn_bwd(const mvfb_bn_desc* d, const void* g, long long ldg, const void* y, long long ldy, const void* x,
            long long ldx, const float* gamma, const float* mean, const float* rstd, void* dx, long long lddx,
-           void* dres, long long lddr, float* dgamma, float* dbeta, float* sums, mvfb_stream_t stream);
+           void* dres, long long lddr, float* dgamma, float* dbeta, float* sums, const unsigned char* relu_mask,
+           mvfb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -126,7 +126,10 @@ size_t mvf_bwd_workspace_bytes(const mvfb_mvf_desc* d) {
   if (!d) return 0;
   // both paths are sized: the fast path can still decline at run time (pointer / stride alignment)
   size_t generic = mvf_generic_bwd_ws(d);
-  size_t fast = mvf_fast_bwd_supported(d) ? 2 * sizeof(float) * (((size_t)d->Cs + 63) / 64 * 64) + mvf_fast_ws(d) : 0;
+  const size_t head = 2 * sizeof(float) * (((size_t)d->Cs + 63) / 64 * 64);
+  size_t fast = mvf_fast_bwd_supported(d) ? head + mvf_fast_ws(d) : 0;
+  const size_t stream = mvf_stream_bwd_supported(d) ? head + mvf_stream_bwd_ws(d) : 0;
+  if (stream > fast) fast = stream;
   return generic > fast ? generic : fast;
 }
 
@@ -201,6 +204,11 @@ int mvf_bwd(const mvfb_mvf_desc* d, const void* g, long long g_stride, const voi
     }
   }
   ws += 2 * sizeof(float) * (((size_t)d->Cs + 63) / 64 * 64);
+  if (mvf_stream_bwd_supported(d)) {
+    rc = mvf_stream_bwd(d, g, g_stride, x, dx, dx_stride, wt, wh, ww, gamma, beta, mean, rstd, dwt, dwh, dww, dgamma,
+                        dbeta, ws, st);
+    if (rc != MVFB_ERR_UNSUPPORTED) return rc;
+  }
   if (mvf_fast_bwd_supported(d)) {
     rc = mvf_fast_bwd(d, g, g_stride, x, dx, dx_stride, wt, wh, ww, gamma, beta, mean, rstd, dwt, dwh, dww, dgamma,
                       dbeta, ws, st);

@@ -98,6 +98,7 @@ bn_stats_kernel(const __nv_bfloat16* __restrict__ x, long long ldx, long long M,
 struct ApplyArgs {
   const __nv_bfloat16 *x, *res;
   __nv_bfloat16* y;
+  uint8_t* mask;                         // optional: 1 bit per element, (y > 0); byte (row, 8-channel vector)
   long long ldx, ldr, ldy, M;
   int C, relu, training;
   float eps, momentum;
@@ -157,6 +158,12 @@ bn_apply_kernel(const ApplyArgs a) {
     if (a.relu) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+      if (a.mask) {
+        uint32_t bits = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bits |= (f[j] > 0.f ? 1u : 0u) << j;
+        a.mask[r * vecs + vec] = (uint8_t)bits;
+      }
     }
     *reinterpret_cast<uint4*>(a.y + r * a.ldy + co) = pack8(f);
   }
@@ -164,6 +171,7 @@ bn_apply_kernel(const ApplyArgs a) {
 
 // ---------------------------------------------------------------- backward
 struct BwdArgs {
+  const uint8_t* mask;                   // ReLU bit mask written by bn_apply (preferred over reading y back)
   const __nv_bfloat16 *g, *y, *x;        // dL/d(out), out (ReLU mask source; null = no ReLU), conv output
   __nv_bfloat16 *dx, *dres;              // dL/d(conv output), dL/d(residual) (null if none)
   long long ldg, ldy, ldx, lddx, lddr, M;
@@ -196,7 +204,11 @@ bn_bwd_reduce_kernel(const BwdArgs a) {
       const uint4 gq = ldg16(a.g + r * a.ldg + co), xq = ldg16(a.x + r * a.ldx + co);
       unpack8(gq, gv);
       unpack8(xq, xv);
-      if (a.y) {
+      if (a.mask) {
+        const uint32_t bits = __ldg(a.mask + r * vecs + vec);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) gv[j] = (bits >> j) & 1u ? gv[j] : 0.f;
+      } else if (a.y) {
         float yv[8];
         unpack8(ldg16(a.y + r * a.ldy + co), yv);
 #pragma unroll
@@ -242,7 +254,11 @@ bn_bwd_apply_kernel(const BwdArgs a) {
     const uint4 gq = ldg16(a.g + r * a.ldg + co), xq = ldg16(a.x + r * a.ldx + co);
     unpack8(gq, gv);
     unpack8(xq, xv);
-    if (a.y) {
+    if (a.mask) {
+      const uint32_t bits = __ldg(a.mask + r * vecs + vec);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) gv[j] = (bits >> j) & 1u ? gv[j] : 0.f;
+    } else if (a.y) {
       float yv[8];
       unpack8(ldg16(a.y + r * a.ldy + co), yv);
 #pragma unroll
@@ -354,7 +370,7 @@ int bn_stats(const mvfb_bn_desc* d, const void* x, long long ldx, float* sums, m
 
 int bn_apply(const mvfb_bn_desc* d, const void* x, long long ldx, const void* residual, long long ldr, void* y,
              long long ldy, const float* sums, const float* gamma, const float* beta, float* running_mean,
-             float* running_var, float* save_mean, float* save_rstd, mvfb_stream_t stream) {
+             float* running_var, float* save_mean, float* save_rstd, unsigned char* relu_mask, mvfb_stream_t stream) {
   int rc = check_bn(d);
   if (rc) return rc;
   MVFB_CHECK(x && y && gamma && beta, MVFB_ERR_ARG, "null x / y / gamma / beta");
@@ -364,6 +380,7 @@ int bn_apply(const mvfb_bn_desc* d, const void* x, long long ldx, const void* re
              "tensors must be 16-byte aligned with ld %% 8 == 0");
   ApplyArgs a;
   a.x = (const __nv_bfloat16*)x; a.res = (const __nv_bfloat16*)residual; a.y = (__nv_bfloat16*)y;
+  a.mask = d->relu ? relu_mask : nullptr;
   a.ldx = ldx; a.ldr = ldr; a.ldy = ldy; a.M = d->M; a.C = d->C; a.relu = d->relu; a.training = d->training;
   a.eps = d->eps; a.momentum = d->momentum; a.sums = sums; a.gamma = gamma; a.beta = beta;
   a.running_mean = running_mean; a.running_var = running_var; a.save_mean = save_mean; a.save_rstd = save_rstd;
@@ -375,19 +392,21 @@ int bn_apply(const mvfb_bn_desc* d, const void* x, long long ldx, const void* re
 
 int bn_bwd(const mvfb_bn_desc* d, const void* g, long long ldg, const void* y, long long ldy, const void* x,
            long long ldx, const float* gamma, const float* mean, const float* rstd, void* dx, long long lddx,
-           void* dres, long long lddr, float* dgamma, float* dbeta, float* sums, mvfb_stream_t stream) {
+           void* dres, long long lddr, float* dgamma, float* dbeta, float* sums, const unsigned char* relu_mask,
+           mvfb_stream_t stream) {
   int rc = check_bn(d);
   if (rc) return rc;
   MVFB_CHECK(g && x && gamma && mean && rstd && dx && dgamma && dbeta && sums, MVFB_ERR_ARG, "null argument");
-  MVFB_CHECK(ok16(g, ldg) && ok16(x, ldx) && ok16(dx, lddx) && (!y || ok16(y, ldy)) && (!dres || ok16(dres, lddr)),
+  MVFB_CHECK(ok16(g, ldg) && ok16(x, ldx) && ok16(dx, lddx) && (!y || relu_mask || ok16(y, ldy)) && (!dres || ok16(dres, lddr)),
              MVFB_ERR_UNSUPPORTED, "tensors must be 16-byte aligned with ld %% 8 == 0");
   cudaStream_t st = (cudaStream_t)stream;
   BwdArgs a;
+  a.mask = d->relu ? relu_mask : nullptr;
   a.g = (const __nv_bfloat16*)g; a.y = d->relu ? (const __nv_bfloat16*)y : nullptr; a.x = (const __nv_bfloat16*)x;
   a.dx = (__nv_bfloat16*)dx; a.dres = (__nv_bfloat16*)dres;
   a.ldg = ldg; a.ldy = ldy; a.ldx = ldx; a.lddx = lddx; a.lddr = lddr; a.M = d->M; a.C = d->C; a.training = d->training;
   a.gamma = gamma; a.mean = mean; a.rstd = rstd; a.sums = sums; a.dgamma = dgamma; a.dbeta = dbeta;
-  MVFB_CHECK(!d->relu || y, MVFB_ERR_ARG, "relu backward needs the forward output y");
+  MVFB_CHECK(!d->relu || y || relu_mask, MVFB_ERR_ARG, "relu backward needs the forward output y or its bit mask");
   MVFB_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * d->C, st));
   static bool once = false;
   if (!once) {

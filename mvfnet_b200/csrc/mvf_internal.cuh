@@ -40,6 +40,14 @@ int mvf_stream_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_s
                    const float* wh, const float* ww, const float* gamma, const float* beta, float* rm, float* rv,
                    float* save_mean, float* save_rstd, void* ws, cudaStream_t st);
 
+// ---- mvf_stream_bwd.cu : bf16 NHWC backward, persistent frame stream (preferred backward path, whole-frame tiles)
+bool mvf_stream_bwd_supported(const mvfb_mvf_desc* d);
+size_t mvf_stream_bwd_ws(const mvfb_mvf_desc* d);
+int mvf_stream_bwd(const mvfb_mvf_desc* d, const void* g, long long g_stride, const void* x, void* dx,
+                   long long dx_stride, const float* wt, const float* wh, const float* ww, const float* gamma,
+                   const float* beta, const float* mean, const float* rstd, float* dwt, float* dwh, float* dww,
+                   float* dgamma, float* dbeta, void* ws, cudaStream_t st);
+
 // sums (fp64, [11][Cs]) -> fp32 parameter gradients (mvf_generic.cu)
 __global__ void mvf_bwd_finalize(const double* sums, int Cs, int h_shares, int w_shares, int has_h, int has_w,
                                  int use_hs, float* dwt, float* dwh, float* dww, float* dgamma, float* dbeta);

@@ -55,10 +55,10 @@ def _L():
         L.bn_stats.restype = C.c_int
         L.bn_stats.argtypes = [C.POINTER(BnDesc), _VP, _LL, _VP, _VP]
         L.bn_apply.restype = C.c_int
-        L.bn_apply.argtypes = [C.POINTER(BnDesc), _VP, _LL, _VP, _LL, _VP, _LL, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]
+        L.bn_apply.argtypes = [C.POINTER(BnDesc), _VP, _LL, _VP, _LL, _VP, _LL, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP, _VP]
         L.bn_bwd.restype = C.c_int
         L.bn_bwd.argtypes = [C.POINTER(BnDesc), _VP, _LL, _VP, _LL, _VP, _LL, _VP, _VP, _VP, _VP, _LL, _VP, _LL, _VP,
-                             _VP, _VP, _VP]
+                             _VP, _VP, _VP, _VP]
         _declared = True
     return L
 
@@ -338,19 +338,23 @@ class _BNAct(torch.autograd.Function):
         rr = _rows(residual) if residual is not None else None
         g32 = gamma if gamma.dtype == torch.float32 else gamma.float()
         b32 = beta if beta.dtype == torch.float32 else beta.float()
+        # ReLU bit mask for the backward (1/16 of y's bytes) -- only when a backward can happen
+        mask = None
+        if relu and any(ctx.needs_input_grad[:3]):
+            mask = torch.empty(xr.shape[0] * (c // 8), dtype=torch.uint8, device=dev)
         rc = L.bn_apply(C.byref(d), ptr(xr), xr.stride(0), ptr(rr), rr.stride(0) if rr is not None else 0, ptr(y), c,
                         ptr(sums), ptr(g32), ptr(b32), ptr(running_mean), ptr(running_var), ptr(save[0]), ptr(save[1]),
-                        _stream())
+                        ptr(mask), _stream())
         _lib.check(rc, "bn_apply")
         yv = y.permute(0, 3, 1, 2)
         ctx.relu, ctx.training, ctx.has_res, ctx.eps = relu, training, residual is not None, eps
-        ctx.save_for_backward(x, yv if relu else None, g32, save)
+        ctx.save_for_backward(x, yv if (relu and mask is None) else None, g32, save, mask)
         return yv
 
     @staticmethod
     def backward(ctx, g):
         L = _L()
-        x, y, gamma, save = ctx.saved_tensors
+        x, y, gamma, save, mask = ctx.saved_tensors
         f, c, h, w = x.shape
         g = g.contiguous(memory_format=torch.channels_last)
         gr, xr = _rows(g), _rows(x)
@@ -364,7 +368,7 @@ class _BNAct(torch.autograd.Function):
         scratch = torch.empty((2, c), dtype=torch.float32, device=dev)
         rc = L.bn_bwd(C.byref(d), ptr(gr), gr.stride(0), ptr(yr), yr.stride(0) if yr is not None else 0, ptr(xr),
                       xr.stride(0), ptr(gamma), ptr(save[0]), ptr(save[1]), ptr(dx), c, ptr(dres), c, ptr(grads[0]),
-                      ptr(grads[1]), ptr(scratch), _stream())
+                      ptr(grads[1]), ptr(scratch), ptr(mask), _stream())
         _lib.check(rc, "bn_bwd")
         dres_v = dres.permute(0, 3, 1, 2) if dres is not None else None
         return dx.permute(0, 3, 1, 2), grads[0], grads[1], None, None, dres_v, None, None, None, None, None
