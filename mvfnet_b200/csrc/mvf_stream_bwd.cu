@@ -50,7 +50,8 @@ struct BArgs {
   BGeo g;
   int use_hs, training, share_h, share_w;
   const float *wt, *wh, *ww, *gamma, *beta, *mean, *rstd;
-  float* partials;        // [grid][2*Cg]: (sum du, sum du*z)
+  float* partials;        // [PA][Cs][2]: (sum du, sum du*z) per clip lane of kernel A
+  int PA;                 // clip lanes of kernel A (rows of `partials`)
   float *dwt, *dwh, *dww, *dgamma, *dbeta;
   __nv_bfloat16* dx;
   long long dx_pix;
@@ -258,7 +259,7 @@ mvf_stream_bwd_reduce(const __grid_constant__ CUtensorMap tmx, const __grid_cons
     const int idx = (ch / V) * (2 * V) + kind * V + (ch % V);
     float v = 0.f;
     for (int wv = 0; wv < cwarps; ++wv) v += c.s_red[wv * 2 * g.Cg + idx];
-    a.partials[(size_t)blockIdx.x * 2 * g.Cg + i] = v;
+    a.partials[((size_t)p * g.Cs + c0) * 2 + i] = v;
   }
 }
 
@@ -300,12 +301,12 @@ mvf_stream_bwd_dx(const __grid_constant__ CUtensorMap tmx, const __grid_constant
   }
   load_coef(c.s_coef, c.s_red, a, c0, nthreads);
   if (a.use_hs) {
-    const int per = 2 * g.Cg, rows = g.P;
+    const int per = 2 * g.Cg, rows = a.PA;
     const int parts = nthreads / per;
     const int k = tid % per, part = tid / per;
     if (part < parts) {
       double acc = 0.0;
-      for (int r = part; r < rows; r += parts) acc += (double)a.partials[((size_t)r * g.ngroups + cg) * per + k];
+      for (int r = part; r < rows; r += parts) acc += (double)a.partials[((size_t)r * g.Cs + c0) * 2 + k];
       c.s_dpart[part * per + k] = acc;
     }
     __syncthreads();
@@ -512,15 +513,16 @@ mvf_stream_bwd_dx(const __grid_constant__ CUtensorMap tmx, const __grid_constant
   }
 }
 
-bool choose_bwd(const mvfb_mvf_desc* d, BGeo& g) {
+// geometry for items of V channels (kernel A: V = 8, kernel B: V = 4); the two kernels tile the channels independently
+bool choose_bwd(const mvfb_mvf_desc* d, int V, bool with_dz, BGeo& g) {
   if (d->dtype != MVFB_BF16 || d->layout != MVFB_NHWC) return false;
   if (d->Cs % 8 != 0 || d->C % 8 != 0 || d->W + 2 > 256 || d->H + 2 > 256) return false;
   const int cands[4] = {64, 32, 16, 8};
   for (int ci = 0; ci < 4; ++ci) {
     const int Cg = cands[ci];
     if (d->Cs % Cg) continue;
-    const int GB = Cg / VB;
-    if (GB > 16) continue;
+    const int GB = Cg / V;
+    if (GB > 16 || GB < 1) continue;
     if (d->H * d->W * GB > kMaxItems) continue;
     g.N = d->N; g.T = d->T; g.Cs = d->Cs; g.H = d->H; g.W = d->W;
     g.Cg = Cg; g.ngroups = d->Cs / Cg;
@@ -537,7 +539,7 @@ bool choose_bwd(const mvfb_mvf_desc* d, BGeo& g) {
     if (P < 1) P = 1;
     if (P > d->N) P = d->N;
     g.P = P;
-    if (smem_bytes(g, true) > (size_t)kSmemLimit) continue;
+    if (smem_bytes(g, with_dz) > (size_t)kSmemLimit) continue;
     return true;
   }
   return false;
@@ -555,28 +557,30 @@ int make_map(CUtensorMap* tm, const void* base, long long pix_stride, const BGeo
 
 bool mvf_stream_bwd_supported(const mvfb_mvf_desc* d) {
   static const bool off = getenv("MVFB_BWD") && getenv("MVFB_BWD")[0] == 'r';   // "ring": tuning experiments
-  BGeo g;
-  return !off && choose_bwd(d, g);
+  BGeo ga, gb;
+  return !off && choose_bwd(d, 8, false, ga) && choose_bwd(d, VB, true, gb);
 }
 
 size_t mvf_stream_bwd_ws(const mvfb_mvf_desc* d) {
-  BGeo g;
-  if (!choose_bwd(d, g)) return 0;
-  return (size_t)g.ngroups * g.P * 2 * g.Cg * sizeof(float) + 256;
+  BGeo ga;
+  if (!choose_bwd(d, 8, false, ga)) return 0;
+  return (size_t)ga.P * d->Cs * 2 * sizeof(float) + 256;
 }
 
 int mvf_stream_bwd(const mvfb_mvf_desc* d, const void* gp, long long g_stride, const void* x, void* dx,
                    long long dx_stride, const float* wt, const float* wh, const float* ww, const float* gamma,
                    const float* beta, const float* mean, const float* rstd, float* dwt, float* dwh, float* dww,
                    float* dgamma, float* dbeta, void* ws, cudaStream_t st) {
-  BGeo g;
-  if (!choose_bwd(d, g)) return MVFB_ERR_UNSUPPORTED;
+  BGeo ga, g;
+  if (!choose_bwd(d, 8, false, ga) || !choose_bwd(d, VB, true, g)) return MVFB_ERR_UNSUPPORTED;
   if (((uintptr_t)x & 15) || ((uintptr_t)gp & 15) || ((uintptr_t)dx & 7) || g_stride % 8 != 0 || dx_stride % 4 != 0)
     return MVFB_ERR_UNSUPPORTED;
-  CUtensorMap tmx, tmg;
+  CUtensorMap tmx, tmg, tmxa, tmga;
   int rc;
   if ((rc = make_map(&tmx, x, d->C, g, true))) return rc;
   if ((rc = make_map(&tmg, gp, g_stride, g, false))) return rc;
+  if ((rc = make_map(&tmxa, x, d->C, ga, true))) return rc;
+  if ((rc = make_map(&tmga, gp, g_stride, ga, false))) return rc;
   const bool has_h = d->mode != MVFB_MODE_T, has_w = d->mode == MVFB_MODE_THW;
   BArgs a;
   a.g = g;
@@ -585,6 +589,7 @@ int mvf_stream_bwd(const mvfb_mvf_desc* d, const void* gp, long long g_stride, c
   a.wt = wt; a.wh = has_h ? wh : nullptr; a.ww = has_w ? ww : nullptr;
   a.gamma = gamma; a.beta = beta; a.mean = mean; a.rstd = rstd;
   a.partials = (float*)ws;
+  a.PA = ga.P;
   a.dwt = dwt; a.dwh = (has_h && !a.share_h) ? dwh : nullptr; a.dww = (has_w && !a.share_w) ? dww : nullptr;
   a.dgamma = dgamma; a.dbeta = dbeta;
   a.dx = (__nv_bfloat16*)dx; a.dx_pix = dx_stride;
@@ -596,8 +601,10 @@ int mvf_stream_bwd(const mvfb_mvf_desc* d, const void* gp, long long g_stride, c
   }
   const dim3 grid(g.ngroups * g.P);
   if (d->use_hs) {
-    const int itemsA = g.H * g.W * (g.Cg / 8);
-    mvf_stream_bwd_reduce<<<grid, 32 * ((itemsA + 31) / 32 + 1), smem_bytes(g, false), st>>>(tmx, tmg, a);
+    BArgs aa = a;
+    aa.g = ga;
+    const int itemsA = ga.H * ga.W * (ga.Cg / 8);
+    mvf_stream_bwd_reduce<<<ga.ngroups * ga.P, 32 * ((itemsA + 31) / 32 + 1), smem_bytes(ga, false), st>>>(tmxa, tmga, aa);
     count_launch();
     MVFB_LAUNCH_CHECK();
   } else {
