@@ -179,7 +179,7 @@ def run_ours(args):
     torch.backends.cudnn.benchmark = True                         # cfg: cudnn_benchmark = True (r50_dense.py:180)
     B = args.batch
     torch.manual_seed(0)
-    model = to_channels_last(build_recognizer(model_cfg(), None, None).to(dev)).train()
+    model = to_channels_last(build_recognizer(model_cfg(DEPTH, T_FRAMES), None, None).to(dev)).train()
     if world > 1:                                                  # MMDistributedDataParallel: broadcast once
         for t in model.state_dict().values():
             dist.broadcast(t, 0)
@@ -315,8 +315,9 @@ def run_ours(args):
     line = {"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "MVFNet-R50 8x8 (T=8) 224x224 synthetic, bf16, train forward+backward+"
-                                   "clip+SGD step, B=%d clips per GPU (BASELINE.json configs[1])" % B,
+            "config": {"workload": "MVFNet-R%d %dx%d (T=%d) 224x224 synthetic, bf16, train forward+backward+"
+                                   "clip+SGD step, B=%d clips per GPU%s" % (DEPTH, T_FRAMES, 64 // T_FRAMES, T_FRAMES, B,
+                                   " (BASELINE.json configs[1])" if (DEPTH, T_FRAMES) == (50, 8) else ""),
                        "clips_per_gpu": B, "frames_per_gpu": B * T_FRAMES, "parallelism": "dp%d" % world,
                        "l2": "no flush: one step streams >10 GB of activations, far above the 126 MB L2"},
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -335,9 +336,15 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--depth", type=int, default=DEPTH, help="ResNet depth (50: BASELINE configs[1]; 101: configs[3])")
+    ap.add_argument("--frames", type=int, default=T_FRAMES, help="frames per clip T (8: configs[1]; 16: configs[2])")
     ap.add_argument("--kernels-only", action="store_true",
                     help="profiling runs (ncu): skip the e2e loop and the cpu_baseline sample")
     args = ap.parse_args()
+    global DEPTH, T_FRAMES, METRIC
+    if (args.depth, args.frames) != (DEPTH, T_FRAMES):
+        DEPTH, T_FRAMES = args.depth, args.frames
+        METRIC = "clips/sec (fwd+bwd) MVFNet-R%d %dx%d 224px" % (DEPTH, T_FRAMES, 64 // T_FRAMES)
     if args.impl == "ours" and not args.kernels_only:
         args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

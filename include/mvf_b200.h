@@ -136,6 +136,8 @@ int conv1x1_wgrad(const mvfb_gemm_desc* d, const void* g, const void* x0, const 
  * ---------------------------------------------------------------------------------------------- */
 typedef struct {
   int F, H, W, Cin, Cout, stride;
+  int ksize;                       /* 3: 3x3 / pad 1 (Bottleneck.conv2);  1: 1x1 / pad 0 with stride 2 -- the strided
+                                      down-sampling convolution of make_res_layer (resnet.py:299-303); w is then (Cout, Cin) */
 } mvfb_conv_desc;
 
 int conv3x3_gemm(const mvfb_conv_desc* d, const void* x, const void* w, void* out, float* colsum, float* colsq,

@@ -41,7 +41,7 @@ struct GemmArgs {
   float* colsq;                    // [N] or null
   // 3x3 convolution as an implicit GEMM (IM2COL kernels): K = 9 * Cin ordered (r, s, c); A tiles are gathered by
   // TMA im2col loads from the NHWC input, M = F * Ho * Wo output pixels
-  int Cin, Ho, Wo, stride;
+  int Cin, Ho, Wo, stride, ks, pad;   // ks = 3 (pad 1) or 1 (pad 0)
 };
 
 template <int BN>
@@ -116,8 +116,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         if (IM2COL) {
           const long long m0 = (long long)mt * BM;
           const int q = (int)(m0 % a.Wo), pq = (int)(m0 / a.Wo);
-          bw = q * a.stride - 1;
-          bh = (pq % a.Ho) * a.stride - 1;
+          bw = q * a.stride - a.pad;
+          bh = (pq % a.Ho) * a.stride - a.pad;
           bn = pq / a.Ho;
           cblocks = a.Cin / BK;
         }
@@ -128,7 +128,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           mbar_arrive_expect_tx(&full[s], C::kStageBytes);
           const int k = kb * BK;
           if (IM2COL) {
-            tma_load_im2col_4d(sa, &tmA1, &full[s], cb * BK, bw, bh, bn, (uint16_t)(rs % 3), (uint16_t)(rs / 3));
+            tma_load_im2col_4d(sa, &tmA1, &full[s], cb * BK, bw, bh, bn, (uint16_t)(rs % a.ks), (uint16_t)(rs / a.ks));
             if (++cb == cblocks) { cb = 0; ++rs; }
           } else {
             tma_load_2d(sa, k < a.K0 ? &tmA0 : &tmA1, &full[s], k, mt * BM);
@@ -288,7 +288,8 @@ int launch(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* 
   GemmArgs a;
   a.M = d->M; a.N = d->N; a.K = d->K; a.K0 = d->K0;
   a.colsum = colsum; a.colsq = colsq;
-  a.Cin = a.Ho = a.Wo = a.stride = 0;
+  a.Cin = a.Ho = a.Wo = a.stride = a.pad = 0;
+  a.ks = 1;
   return launch_kernel<BN, false>(tmA0, tmA1, tmB, tmD, a, st);
 }
 
@@ -300,18 +301,19 @@ int launch_conv3x3(const mvfb_conv_desc* d, const void* x, const void* w, void* 
   CUtensorMap tmA, tmB, tmD;
   const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->F};
   const uint64_t strides[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
-  const int lower[2] = {-1, -1}, upper[2] = {-1, -1};          // pad 1; upper = pad - (kernel - 1)
+  const int pad = d->ksize == 3 ? 1 : 0, taps = d->ksize * d->ksize;
+  const int lower[2] = {-pad, -pad}, upper[2] = {-pad, -pad};  // upper corner = pad - (kernel - 1)
   const uint32_t estr[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
   int rc = encode_tmap_im2col(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, lower, upper, BK, BM, estr,
                               CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   const long long M = (long long)d->F * Ho * Wo;
-  if ((rc = make_2d_map(&tmB, w, (uint64_t)9 * d->Cin, (uint64_t)d->Cout, (uint64_t)9 * d->Cin, BK, BN))) return rc;
+  if ((rc = make_2d_map(&tmB, w, (uint64_t)taps * d->Cin, (uint64_t)d->Cout, (uint64_t)taps * d->Cin, BK, BN))) return rc;
   if ((rc = make_2d_map(&tmD, out, (uint64_t)d->Cout, (uint64_t)M, (uint64_t)d->Cout, 64, BM))) return rc;
   GemmArgs a;
-  a.M = M; a.N = d->Cout; a.K = 9 * d->Cin; a.K0 = 0;
+  a.M = M; a.N = d->Cout; a.K = taps * d->Cin; a.K0 = 0;
   a.colsum = colsum; a.colsq = colsq;
-  a.Cin = d->Cin; a.Ho = Ho; a.Wo = Wo; a.stride = d->stride;
+  a.Cin = d->Cin; a.Ho = Ho; a.Wo = Wo; a.stride = d->stride; a.ks = d->ksize; a.pad = pad;
   return launch_kernel<BN, true>(tmA, tmA, tmB, tmD, a, st);
 }
 
@@ -343,8 +345,8 @@ extern "C" int conv1x1_gemm(const mvfb_gemm_desc* d, const void* a0, const void*
 extern "C" int conv3x3_gemm(const mvfb_conv_desc* d, const void* x, const void* w, void* out, float* colsum,
                             float* colsq, mvfb_stream_t stream) {
   MVFB_CHECK(d && x && w && out, MVFB_ERR_ARG, "null descriptor / operand");
-  MVFB_CHECK(d->F > 0 && d->H > 0 && d->W > 0 && (d->stride == 1 || d->stride == 2), MVFB_ERR_ARG,
-             "bad conv shape F=%d H=%d W=%d stride=%d", d->F, d->H, d->W, d->stride);
+  MVFB_CHECK(d->F > 0 && d->H > 0 && d->W > 0 && (d->stride == 1 || d->stride == 2) && (d->ksize == 3 || d->ksize == 1),
+             MVFB_ERR_ARG, "bad conv shape F=%d H=%d W=%d stride=%d ksize=%d", d->F, d->H, d->W, d->stride, d->ksize);
   MVFB_CHECK(d->Cin % BK == 0 && d->Cout % 64 == 0, MVFB_ERR_UNSUPPORTED, "Cin=%d and Cout=%d must be multiples of 64",
              d->Cin, d->Cout);
   MVFB_CHECK((colsum == nullptr) == (colsq == nullptr), MVFB_ERR_ARG, "colsum and colsq go together");

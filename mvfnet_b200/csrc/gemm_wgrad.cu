@@ -36,7 +36,7 @@ struct WArgs {
   int pblocks;                     // ceil(M / 64)
   float* dw;
   long long lddw;
-  int Ho, Wo, stride;              // IM2COL (3x3 / pad 1): output geometry; dw is (Cout, 3, 3, Cin)
+  int Ho, Wo, stride, ks, pad;     // IM2COL (3x3 / pad 1 or 1x1 / pad 0): output geometry; dw is (Cout, ks, ks, Cin)
 };
 
 template <int BN>
@@ -119,11 +119,11 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BKP * 128), &tmG, &full[s], nt * BM + j * 64, p);
         if (IM2COL) {
           const int q = p % a.Wo, pq = p / a.Wo;                // first output pixel of the block -> window origin
-          const int bw = q * a.stride - 1, bh = (pq % a.Ho) * a.stride - 1, bn = pq / a.Ho;
+          const int bw = q * a.stride - a.pad, bh = (pq % a.Ho) * a.stride - a.pad, bn = pq / a.Ho;
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j)
             tma_load_im2col_4d(sa + C::kABytes + j * (BKP * 128), &tmX1, &full[s], ct * BN + j * 64, bw, bh, bn,
-                               (uint16_t)(rs % 3), (uint16_t)(rs / 3));
+                               (uint16_t)(rs % a.ks), (uint16_t)(rs / a.ks));
         } else {
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j) {
@@ -195,7 +195,7 @@ int launch_wgrad_kernel(const CUtensorMap& tmG, const CUtensorMap& tmX0, const C
                         cudaStream_t st) {
   using C = WCfg<BN>;
   a.n_tiles = (a.N + BM - 1) / BM;
-  a.k_tiles = (a.K / BN) * (IM2COL ? 9 : 1);
+  a.k_tiles = (a.K / BN) * (IM2COL ? a.ks * a.ks : 1);
   a.pblocks = (int)((a.M + BKP - 1) / BKP);
   const int tiles = a.n_tiles * a.k_tiles;
   int splits = (2 * num_sms() + tiles - 1) / tiles;            // ~2 CTAs worth of work items per SM
@@ -228,7 +228,8 @@ int launch_wgrad(const mvfb_gemm_desc* d, const void* g, const void* x0, const v
   WArgs a;
   a.M = d->M; a.N = d->N; a.K = d->K; a.K0 = d->K0;
   a.dw = dw; a.lddw = d->ldd;
-  a.Ho = a.Wo = a.stride = 0;
+  a.Ho = a.Wo = a.stride = a.pad = 0;
+  a.ks = 1;
   return launch_wgrad_kernel<BN, false>(tmG, tmX0, tmX1, a, (size_t)d->N * d->ldd, st);
 }
 
@@ -242,16 +243,17 @@ int launch_wgrad3x3(const mvfb_conv_desc* d, const void* g, const void* x, float
   if ((rc = map_64x64(&tmG, g, (uint64_t)d->Cout, (uint64_t)M, (uint64_t)d->Cout))) return rc;
   const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->F};
   const uint64_t strides[3] = {(uint64_t)d->Cin * 2, (uint64_t)d->W * d->Cin * 2, (uint64_t)d->H * d->W * d->Cin * 2};
-  const int lower[2] = {-1, -1}, upper[2] = {-1, -1};
+  const int pad = d->ksize == 3 ? 1 : 0, taps = d->ksize * d->ksize;
+  const int lower[2] = {-pad, -pad}, upper[2] = {-pad, -pad};
   const uint32_t estr[4] = {1, (uint32_t)d->stride, (uint32_t)d->stride, 1};
   if ((rc = encode_tmap_im2col(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dims, strides, lower, upper, 64, BKP, estr,
                                CU_TENSOR_MAP_SWIZZLE_128B)))
     return rc;
   WArgs a;
   a.M = M; a.N = d->Cout; a.K = d->Cin; a.K0 = 0;
-  a.dw = dw; a.lddw = 9LL * d->Cin;
-  a.Ho = Ho; a.Wo = Wo; a.stride = d->stride;
-  return launch_wgrad_kernel<BN, true>(tmG, tmX, tmX, a, (size_t)d->Cout * 9 * d->Cin, st);
+  a.dw = dw; a.lddw = (long long)taps * d->Cin;
+  a.Ho = Ho; a.Wo = Wo; a.stride = d->stride; a.ks = d->ksize; a.pad = pad;
+  return launch_wgrad_kernel<BN, true>(tmG, tmX, tmX, a, (size_t)d->Cout * taps * d->Cin, st);
 }
 
 }  // namespace
@@ -282,8 +284,8 @@ extern "C" int conv1x1_wgrad(const mvfb_gemm_desc* d, const void* g, const void*
 // g: (F, Ho, Wo, Cout) bf16; x: (F, H, W, Cin) bf16; dw: (Cout, 3, 3, Cin) fp32, zeroed by the call.
 extern "C" int conv3x3_wgrad(const mvfb_conv_desc* d, const void* g, const void* x, float* dw, mvfb_stream_t stream) {
   MVFB_CHECK(d && g && x && dw, MVFB_ERR_ARG, "null descriptor / operand");
-  MVFB_CHECK(d->F > 0 && d->H > 0 && d->W > 0 && (d->stride == 1 || d->stride == 2), MVFB_ERR_ARG,
-             "bad conv shape F=%d H=%d W=%d stride=%d", d->F, d->H, d->W, d->stride);
+  MVFB_CHECK(d->F > 0 && d->H > 0 && d->W > 0 && (d->stride == 1 || d->stride == 2) && (d->ksize == 3 || d->ksize == 1),
+             MVFB_ERR_ARG, "bad conv shape F=%d H=%d W=%d stride=%d ksize=%d", d->F, d->H, d->W, d->stride, d->ksize);
   MVFB_CHECK(d->Cin % 64 == 0 && d->Cout % 64 == 0, MVFB_ERR_UNSUPPORTED, "Cin=%d and Cout=%d must be multiples of 64",
              d->Cin, d->Cout);
   MVFB_CHECK(!((uintptr_t)g & 15) && !((uintptr_t)x & 15) && !((uintptr_t)dw & 15), MVFB_ERR_UNSUPPORTED,

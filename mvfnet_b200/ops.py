@@ -27,7 +27,7 @@ class GemmDesc(C.Structure):
 
 class ConvDesc(C.Structure):
     """mvfb_conv_desc (include/mvf_b200.h)."""
-    _fields_ = [(n, C.c_int) for n in ("F", "H", "W", "Cin", "Cout", "stride")]
+    _fields_ = [(n, C.c_int) for n in ("F", "H", "W", "Cin", "Cout", "stride", "ksize")]
 
 
 class BnDesc(C.Structure):
@@ -247,7 +247,7 @@ def conv3x3_raw(x, w_krsc, stride, stats=False):
     cout = w_krsc.shape[0]
     ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
     d = ConvDesc()
-    d.F, d.H, d.W, d.Cin, d.Cout, d.stride = f, h, w, cin, cout, stride
+    d.F, d.H, d.W, d.Cin, d.Cout, d.stride, d.ksize = f, h, w, cin, cout, stride, (3 if w_krsc.dim() == 4 else 1)
     out = torch.empty((f, ho, wo, cout), dtype=torch.bfloat16, device=x.device)
     sums = torch.zeros((2, cout), dtype=torch.float32, device=x.device) if stats else None
     rc = L.conv3x3_gemm(C.byref(d), ptr(x), ptr(w_krsc), ptr(out), ptr(sums[0]) if stats else None,
@@ -285,7 +285,7 @@ class _Conv3x3(torch.autograd.Function):
         if need_dw and wgrad_enabled() and (x.shape[1] >= 256 or os.environ.get("MVFB_WGRAD3X3") == "all"):
             f, cin, h, w = x.shape
             d = ConvDesc()
-            d.F, d.H, d.W, d.Cin, d.Cout, d.stride = f, h, w, cin, wb.shape[0], st
+            d.F, d.H, d.W, d.Cin, d.Cout, d.stride, d.ksize = f, h, w, cin, wb.shape[0], st, 3
             dwk = torch.empty((wb.shape[0], 3, 3, cin), dtype=torch.float32, device=x.device)
             _lib.check(_L().conv3x3_wgrad(C.byref(d), ptr(g), ptr(x), ptr(dwk), _stream()), "conv3x3_wgrad")
             dw = dwk.permute(0, 3, 1, 2)                                  # (Cout, Cin, 3, 3) view of the KRSC buffer
@@ -299,6 +299,48 @@ class _Conv3x3(torch.autograd.Function):
             if need_dw:
                 dw = r[1].float()
         return dx, dw, None, None
+
+
+class _Conv1x1Strided(torch.autograd.Function):
+    """The stride-2 1x1 down-sampling convolution (make_res_layer, resnet.py:299-303): forward and weight gradient
+    gather the strided pixels with TMA im2col (1x1 window); the input gradient is the plain GEMM on the compact
+    gradient, scattered to the even pixels of a zeroed tensor."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride, stats):
+        cout, cin = weight.shape[0], weight.shape[1]
+        wb = weight.detach().reshape(cout, cin).to(torch.bfloat16)
+        y, sums = conv3x3_raw(x, wb, stride, stats)
+        ctx.stride = stride
+        ctx.save_for_backward(x, wb)
+        if not stats:
+            return y
+        ctx.mark_non_differentiable(sums)
+        return y, sums
+
+    @staticmethod
+    def backward(ctx, g, *unused):
+        x, wb = ctx.saved_tensors
+        st = ctx.stride
+        f, cin, h, w = x.shape
+        g = g.contiguous(memory_format=torch.channels_last)
+        dx = dw = None
+        if ctx.needs_input_grad[0]:
+            dxc, _, _ = gemm_tn(_rows(g), wb.t().contiguous())                       # (F*Ho*Wo, Cin)
+            dx = torch.zeros((f, h, w, cin), dtype=torch.bfloat16, device=x.device)
+            dx[:, ::st, ::st, :] = dxc.view(f, g.shape[2], g.shape[3], cin)
+            dx = dx.permute(0, 3, 1, 2)
+        if ctx.needs_input_grad[1]:
+            d = ConvDesc()
+            d.F, d.H, d.W, d.Cin, d.Cout, d.stride, d.ksize = f, h, w, cin, wb.shape[0], st, 1
+            dwk = torch.empty((wb.shape[0], cin), dtype=torch.float32, device=x.device)
+            _lib.check(_L().conv3x3_wgrad(C.byref(d), ptr(g), ptr(x), ptr(dwk), _stream()), "conv3x3_wgrad")
+            dw = dwk.view(wb.shape[0], cin, 1, 1)
+        return dx, dw, None, None
+
+
+def conv1x1_strided(x, weight, stride, stats=False):
+    return _Conv1x1Strided.apply(x, weight, stride, stats)
 
 
 def conv3x3(x, weight, stride=1, stats=False):

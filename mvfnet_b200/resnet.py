@@ -42,6 +42,12 @@ def _conv1x1(conv, x, want_stats=False):
         if want_stats:
             return ops.conv1x1(x, conv.weight, True)
         return ops.conv1x1(x, conv.weight), None
+    if (type(conv) is nn.Conv2d and conv.kernel_size == (1, 1) and conv.stride == (2, 2) and conv.bias is None
+            and conv.groups == 1 and conv.padding == (0, 0) and ops.conv3x3_enabled()
+            and ops.eligible(x, conv.in_channels, conv.out_channels) and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0):
+        if want_stats:
+            return ops.conv1x1_strided(x, conv.weight, 2, True)
+        return ops.conv1x1_strided(x, conv.weight, 2), None
     return conv(x), None
 
 

@@ -209,3 +209,24 @@ def test_wgrad_mn_major_gemm(M, N, K, K0):
     ref = dy.float().t() @ xcat
     assert dw.dtype == torch.float32 and dw.shape == ref.shape
     assert rel(dw, ref) < 2e-3
+
+
+@pytest.mark.parametrize("F,Cin,Cout,H", [(4, 256, 512, 56), (8, 512, 1024, 28), (8, 1024, 2048, 14)])
+def test_strided_1x1_downsample(F, Cin, Cout, H):
+    """make_res_layer's stride-2 1x1 convolution: im2col (1x1 window) forward + weight gradient, GEMM + scatter dgrad."""
+    from mvfnet_b200 import ops
+    torch.backends.cudnn.allow_tf32 = True
+    g = torch.Generator(device="cuda").manual_seed(F + Cin)
+    x = torch.randn(F, Cin, H, H, device="cuda", generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, 1, 1, device="cuda", generator=g) / Cin ** 0.5).bfloat16()
+    xr, wr = x.float().requires_grad_(True), w.float().requires_grad_(True)
+    ref = torch.nn.functional.conv2d(xr, wr, None, 2)
+    gy = torch.randn_like(ref)
+    ref.backward(gy)
+    xo, wo = x.clone().requires_grad_(True), w.float().clone().requires_grad_(True)
+    y, sums = ops.conv1x1_strided(xo, wo, 2, True)
+    y.backward(gy.bfloat16().contiguous(memory_format=torch.channels_last))
+    assert rel(y.detach(), ref.detach()) < 1e-2
+    assert rel(sums[1], (y.detach().float() ** 2).sum((0, 2, 3))) < 1e-3
+    assert rel(xo.grad, xr.grad) < 2e-2
+    assert rel(wo.grad, wr.grad) < 2e-2
