@@ -329,6 +329,7 @@ def run_ours(args):
 
 
 def main():
+    global DEPTH, T_FRAMES, METRIC
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -341,7 +342,6 @@ def main():
     ap.add_argument("--kernels-only", action="store_true",
                     help="profiling runs (ncu): skip the e2e loop and the cpu_baseline sample")
     args = ap.parse_args()
-    global DEPTH, T_FRAMES, METRIC
     if (args.depth, args.frames) != (DEPTH, T_FRAMES):
         DEPTH, T_FRAMES = args.depth, args.frames
         METRIC = "clips/sec (fwd+bwd) MVFNet-R%d %dx%d 224px" % (DEPTH, T_FRAMES, 64 // T_FRAMES)
