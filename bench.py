@@ -305,7 +305,10 @@ def run_ours(args):
     a_f, us_f, n_f = agg(fwd)
     a_b, us_b, n_b = agg(bwd)
     roofline = {"bound": "hbm", "kernel": "mvf_fwd (fused T/H/W stencil + BN3d + hardswish)", "achieved": a_f,
-                "peak": peak, "unit": "GB/s", "frac": (a_f / peak) if a_f else None, "traffic": None,
+                "peak": peak, "unit": "GB/s", "frac": (a_f / peak) if a_f else None,
+                # ncu --set full (profiles/r01_mvf_v3_stream_ncu_full.csv): dram read+write of the stats+apply pair is
+                # 1.015x the algorithmic bytes (second pass served by L2); scaled to this run's mean launch
+                "traffic": (1.015 * sum(r[0] for r in fwd) / len(fwd)) if fwd else None,
                 "peak_source": peak_src, "launches_timed": n_f, "avg_launch_us": us_f,
                 "algorithmic_bytes": "2*E*s per launch (E = B*T*Cs*H*W slab elements, s = 2 B bf16), summed over "
                                      "the 9 MVF modules of R50",
@@ -323,6 +326,11 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+    if (DEPTH, T_FRAMES) == (50, 8):
+        # per-layer max(tensor time, min HBM traffic time) bound of the conv stack, fwd+bwd
+        bound = 4680.0 * world
+        line["conv_roofline"] = {"bound_clips_per_s": bound, "frac": value / bound,
+                                 "how": "BASELINE.md: sum over conv layers of max(2*MACs/1383 TF/s, min bf16 bytes/6453 GB/s), x3 for fwd+bwd"}
     if cpu is not None:
         line["cpu_baseline"] = cpu
     print(json.dumps(line))

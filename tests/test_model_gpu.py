@@ -109,3 +109,30 @@ def test_whole_model_bf16_channels_last_runs():
     assert abs(loss.item() - float(z["train_loss"])) < 3e-2 * abs(float(z["train_loss"]))
     for k, p in m.named_parameters():
         assert p.grad is not None and torch.isfinite(p.grad).all(), k
+
+
+def test_whole_model_bf16_eval_and_fcn_testing():
+    """Inference path (BASELINE configs[4] style): eval-mode BN through the fused kernels in bf16, plain and fcn_testing
+    heads (tsn_clshead.py:99-117 folds to mean + linear), against the reference's fp32 eval probabilities."""
+    from mvfnet_b200 import build_recognizer, _lib
+    from mvfnet_b200.utils import to_channels_last
+    z = np.load(GOLDEN + "/model_r50.npz")
+    depth, t, b, px, seed = [int(v) for v in z["meta"]]
+    m = build_recognizer(model_cfg(depth, t, 0.0), None, dict(average_clips="prob"))
+    m.load_state_dict(synth_state_dict(seed, depth=depth, n_segment=t))
+    m = to_channels_last(m.cuda()).eval()
+    img = torch.from_numpy(z["img"]).cuda()
+    before = _lib.launch_count()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        prob = m(img, None, return_loss=False)
+        m.fcn_testing = True
+        m.cls_head.fcn_testing = True
+        prob_fcn = m(img, None, return_loss=False)
+    assert _lib.launch_count() - before > 100, "the fused kernels were not used"
+    ref = z["eval_prob"]
+    assert prob.shape == ref.shape and abs(prob.sum() - 1.0) < 1e-3
+    # 400-way softmax of a random-weight net (near-uniform: the arg-max is a coin toss between near-ties, so compare the
+    # distributions): L1 distance and largest per-class deviation relative to the largest probability
+    for got in (prob, prob_fcn):
+        assert np.abs(got - ref).sum() < 5e-2, np.abs(got - ref).sum()
+        assert np.abs(got - ref).max() < 5e-2 * ref.max(), (np.abs(got - ref).max(), ref.max())
