@@ -131,8 +131,13 @@ def test_whole_model_bf16_eval_and_fcn_testing():
     assert _lib.launch_count() - before > 100, "the fused kernels were not used"
     ref = z["eval_prob"]
     assert prob.shape == ref.shape and abs(prob.sum() - 1.0) < 1e-3
-    # 400-way softmax of a random-weight net (near-uniform: the arg-max is a coin toss between near-ties, so compare the
-    # distributions): L1 distance and largest per-class deviation relative to the largest probability
+    # The synthetic weights give logits of O(100): the fp32 softmax is nearly one-hot and a 1 % bf16 perturbation of the
+    # logits moves probability mass between the top classes, so the distribution is compared through its top class and
+    # the mass the reference's top-5 classes receive; the two bf16 heads (per-frame linear then mean vs fcn: mean then
+    # 1x1x1 conv) are algebraically identical in eval mode and must agree tightly.
+    top5 = np.argsort(ref[0])[-5:]
     for got in (prob, prob_fcn):
-        assert np.abs(got - ref).sum() < 5e-2, np.abs(got - ref).sum()
-        assert np.abs(got - ref).max() < 5e-2 * ref.max(), (np.abs(got - ref).max(), ref.max())
+        assert got.argmax() == ref.argmax()
+        assert abs(got[0, top5].sum() - ref[0, top5].sum()) < 0.1
+        assert np.abs(got - ref).sum() < 0.5
+    assert np.abs(prob - prob_fcn).sum() < 3e-2
