@@ -142,6 +142,10 @@ mvf_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const StreamArgs 
     s_red[view * g.Cg + ch] = w1;                              // middle taps, summed below
   }
   if (PASS == PASS_TRAIN) {
+    // Programmatic dependent launch: this grid may start while the statistics grid is still draining (its barrier
+    // setup, first TMA loads of x and coefficient loads above overlap that tail); the partial sums are only valid
+    // once the primary grid has completed and flushed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int per = 2 * g.Cg, rows = g.hsplit * g.P;          // partial rows of this channel group
     const int parts = nthreads / per;
     const int k = tid % per, part = tid / per;
@@ -197,6 +201,7 @@ mvf_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmx, const StreamArgs 
 
   FV<V> sum = zerov<V>(), sq = zerov<V>();
   const int vec = tid % g.G;
+  if (PASS == PASS_STATS) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // let the apply grid queue up
   if ((a.debug & 4) && tid == 0) stamps[1] = gtimer();
 
   if (producer) {
@@ -392,7 +397,14 @@ int launch_stream(const mvfb_mvf_desc* d, const CUtensorMap& tmx, const StreamAr
     mvf_stream_fwd_kernel<PASS_STATS, V><<<grid, block, smem, st>>>(tmx, a);
     count_launch();
     MVFB_LAUNCH_CHECK();
-    mvf_stream_fwd_kernel<PASS_TRAIN, V><<<grid, block, smem, st>>>(tmx, a);
+    // second pass as a programmatic dependent launch (PDL): no host-visible gap between the two grids
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    MVFB_CUDA(cudaLaunchKernelEx(&cfg, mvf_stream_fwd_kernel<PASS_TRAIN, V>, tmx, a));
   } else {
     mvf_stream_fwd_kernel<PASS_APPLY, V><<<grid, block, smem, st>>>(tmx, a);
   }

@@ -162,6 +162,7 @@ mvf_stream_bwd_reduce(const __grid_constant__ CUtensorMap tmx, const __grid_cons
 
   FV<V> sum = zerov<V>(), sq = zerov<V>();
   const int vec = tid % G;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");     // the dx kernel may queue up behind this grid
   if (producer) {
     if (lane == 0) {
       int s = 0, use = 1, n = p, t = 0;
@@ -301,6 +302,9 @@ mvf_stream_bwd_dx(const __grid_constant__ CUtensorMap tmx, const __grid_constant
   }
   load_coef(c.s_coef, c.s_red, a, c0, nthreads);
   if (a.use_hs) {
+    // launched as a programmatic dependent of the reduce kernel: everything above overlapped its tail; its partial
+    // rows, its zeroing of dw*, and the last reads of g (which dx may alias) are complete after this wait
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     const int per = 2 * g.Cg, rows = a.PA;
     const int parts = nthreads / per;
     const int k = tid % per, part = tid / per;
@@ -613,7 +617,14 @@ int mvf_stream_bwd(const mvfb_mvf_desc* d, const void* gp, long long g_stride, c
     if (a.dww) MVFB_CUDA(cudaMemsetAsync(a.dww, 0, sizeof(float) * 3 * d->Cs, st));
   }
   const int itemsB = g.H * g.W * (g.Cg / VB);
-  mvf_stream_bwd_dx<<<grid, 32 * ((itemsB + 31) / 32 + 1), smem_bytes(g, true), st>>>(tmx, tmg, a);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = dim3(32 * ((itemsB + 31) / 32 + 1)); cfg.dynamicSmemBytes = smem_bytes(g, true);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = d->use_hs ? 1 : 0;   // PDL behind the reduce kernel only
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  MVFB_CUDA(cudaLaunchKernelEx(&cfg, mvf_stream_bwd_dx, tmx, tmg, a));
   count_launch();
   MVFB_LAUNCH_CHECK();
   return MVFB_OK;
