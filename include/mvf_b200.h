@@ -71,6 +71,9 @@ size_t mvf_bwd_workspace_bytes(const mvfb_mvf_desc* d);
  *   NHWC: y[((f*H + h)*W + w)*y_stride + c]    (y_stride = C or Cs)
  * x is never modified (it is the residual identity, backbones/resnet.py:211).
  * wt/wh/ww: fp32 (Cs,3) taps = shift_conv/h_conv/w_conv weights; wh/ww ignored per `mode`.
+ * dtype MVFB_BF16: each of the nine taps is rounded to bf16 before use, in the forward and in the backward
+ * alike (what torch.autocast(bfloat16) does to the reference's Conv3d weights); accumulation, BatchNorm and
+ * HardSwish are fp32.  dtype MVFB_F32 uses the taps as given.
  * gamma/beta/running_*: fp32 (Cs); save_mean/save_rstd: fp32 (Cs) outputs (training; may be NULL
  * in eval).  training: running_mean/var are updated in place with momentum (unbiased variance).
  */
@@ -84,6 +87,8 @@ int mvf_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_stride, 
  * Outputs dwt/dwh/dww (Cs,3) fp32, dgamma/dbeta (Cs) fp32 are OVERWRITTEN.  With share (wh==wt and/or
  * ww==wt) the views' tap gradients are summed into dwt and dwh/dww may be NULL.
  * training: save_mean/save_rstd from the forward; eval: running stats.
+ * The library owns one 512-byte device allocation per GPU (grid-barrier words of the single-launch train-mode
+ * forward, created on first use, never freed); every other buffer is the caller's.
  * dx MAY alias g (same pointer and stride): every kernel reads a frame of g completely before that frame's
  * dx is written -- this is how the caller turns "dL/dx' for all C channels" into dL/dx in place.
  */

@@ -119,6 +119,8 @@ size_t mvf_fwd_workspace_bytes(const mvfb_mvf_desc* d) {
   size_t fast = mvf_fast_supported(d) ? mvf_fast_ws(d) : 0;
   size_t stream = mvf_stream_ws(d);
   if (stream > fast) fast = stream;
+  const size_t sweep = mvf_sweep_ws(d);
+  if (sweep > fast) fast = sweep;
   return generic > fast ? generic : fast;
 }
 
@@ -149,7 +151,12 @@ int mvf_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_stride, 
   MVFB_CHECK(workspace_bytes >= mvf_fwd_workspace_bytes(d) && workspace, MVFB_ERR_WORKSPACE,
              "workspace too small: %zu < %zu", workspace_bytes, mvf_fwd_workspace_bytes(d));
   cudaStream_t st = (cudaStream_t)stream;
-  static const char* prefer = getenv("MVFB_FWD");             // tuning experiments: "ring" skips the stream kernel
+  static const char* prefer = getenv("MVFB_FWD");             // tuning experiments: "stream" / "ring" skip newer kernels
+  if (!prefer && mvf_sweep_supported(d)) {
+    rc = mvf_sweep_fwd(d, x, y, y_stride, wt, wh, ww, gamma, beta, running_mean, running_var, save_mean, save_rstd,
+                       workspace, st);
+    if (rc != MVFB_ERR_UNSUPPORTED) return rc;
+  }
   if (!(prefer && prefer[0] == 'r') && mvf_stream_supported(d)) {
     rc = mvf_stream_fwd(d, x, y, y_stride, wt, wh, ww, gamma, beta, running_mean, running_var, save_mean, save_rstd,
                         workspace, st);

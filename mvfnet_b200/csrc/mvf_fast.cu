@@ -82,10 +82,10 @@ struct Coef {
 #pragma unroll
     for (int j = 0; j < V; ++j) {
       const int c3 = (ch0 + j) * 3;
-      t0[j] = wt[c3]; c[j] = wt[c3 + 1]; t2[j] = wt[c3 + 2];
+      t0[j] = round_bf16(wt[c3]); c[j] = round_bf16(wt[c3 + 1]); t2[j] = round_bf16(wt[c3 + 2]);
       h0[j] = h2[j] = w0[j] = w2[j] = 0.f;
-      if (wh) { h0[j] = wh[c3]; c[j] += wh[c3 + 1]; h2[j] = wh[c3 + 2]; }
-      if (ww) { w0[j] = ww[c3]; c[j] += ww[c3 + 1]; w2[j] = ww[c3 + 2]; }
+      if (wh) { h0[j] = round_bf16(wh[c3]); c[j] += round_bf16(wh[c3 + 1]); h2[j] = round_bf16(wh[c3 + 2]); }
+      if (ww) { w0[j] = round_bf16(ww[c3]); c[j] += round_bf16(ww[c3 + 1]); w2[j] = round_bf16(ww[c3 + 2]); }
     }
   }
 };
@@ -388,10 +388,10 @@ struct Coef8 {
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
       const int c3 = (ch0 + j) * 3;
-      a[1][j] = wt[c3]; a[0][j] = wt[c3 + 1]; a[2][j] = wt[c3 + 2];
+      a[1][j] = round_bf16(wt[c3]); a[0][j] = round_bf16(wt[c3 + 1]); a[2][j] = round_bf16(wt[c3 + 2]);
       a[3][j] = a[4][j] = a[5][j] = a[6][j] = 0.f;
-      if (wh) { a[3][j] = wh[c3]; a[0][j] += wh[c3 + 1]; a[4][j] = wh[c3 + 2]; }
-      if (ww) { a[5][j] = ww[c3]; a[0][j] += ww[c3 + 1]; a[6][j] = ww[c3 + 2]; }
+      if (wh) { a[3][j] = round_bf16(wh[c3]); a[0][j] += round_bf16(wh[c3 + 1]); a[4][j] = round_bf16(wh[c3 + 2]); }
+      if (ww) { a[5][j] = round_bf16(ww[c3]); a[0][j] += round_bf16(ww[c3 + 1]); a[6][j] = round_bf16(ww[c3 + 2]); }
     }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {

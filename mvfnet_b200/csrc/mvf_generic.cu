@@ -6,6 +6,7 @@
 
 #include "common.cuh"
 #include "mvf_internal.cuh"
+#include "ptx.cuh"
 
 namespace mvfb {
 
@@ -50,12 +51,19 @@ struct Taps {
   float t0, t1, t2, h0, h1, h2, w0, w1, w2;
 };
 
+// bf16 activations imply bf16 taps (see round_bf16 in ptx.cuh); fp32 activations use the taps as given.
+template <typename T>
 __device__ __forceinline__ Taps load_taps(const float* wt, const float* wh, const float* ww, int c) {
   Taps k;
   k.t0 = wt[c * 3 + 0]; k.t1 = wt[c * 3 + 1]; k.t2 = wt[c * 3 + 2];
   k.h0 = k.h1 = k.h2 = k.w0 = k.w1 = k.w2 = 0.f;
   if (wh) { k.h0 = wh[c * 3 + 0]; k.h1 = wh[c * 3 + 1]; k.h2 = wh[c * 3 + 2]; }
   if (ww) { k.w0 = ww[c * 3 + 0]; k.w1 = ww[c * 3 + 1]; k.w2 = ww[c * 3 + 2]; }
+  if (sizeof(T) == 2) {
+    k.t0 = round_bf16(k.t0); k.t1 = round_bf16(k.t1); k.t2 = round_bf16(k.t2);
+    k.h0 = round_bf16(k.h0); k.h1 = round_bf16(k.h1); k.h2 = round_bf16(k.h2);
+    k.w0 = round_bf16(k.w0); k.w1 = round_bf16(k.w1); k.w2 = round_bf16(k.w2);
+  }
   return k;
 }
 
@@ -127,7 +135,7 @@ struct GenParams {
 template <typename T>
 __global__ void __launch_bounds__(256) gen_fwd_stats(const T* __restrict__ x, GenParams p) {
   const int c = blockIdx.x, n = blockIdx.y;
-  const Taps k = load_taps(p.wt, p.wh, p.ww, c);
+  const Taps k = load_taps<T>(p.wt, p.wh, p.ww, c);
   const T* base = x + (long long)n * p.T * p.sx.f + c * p.sx.c;
   const int vol = p.T * p.H * p.W;
   float acc[2] = {0.f, 0.f};
@@ -171,7 +179,7 @@ __device__ __forceinline__ void bn_coeffs(const GenParams& p, int c, bool writer
 template <typename T>
 __global__ void __launch_bounds__(256) gen_fwd_apply(const T* __restrict__ x, T* __restrict__ y, GenParams p) {
   const int c = blockIdx.x, n = blockIdx.y;
-  const Taps k = load_taps(p.wt, p.wh, p.ww, c);
+  const Taps k = load_taps<T>(p.wt, p.wh, p.ww, c);
   float scale = 1.f, shift = 0.f;
   if (p.use_hs) {
     float mean, rstd;
@@ -203,7 +211,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) gen_bwd_reduce(const T* __restrict__ g, const T* __restrict__ x, GenBwdParams q) {
   const GenParams& p = q.f;
   const int c = blockIdx.x, n = blockIdx.y;
-  const Taps k = load_taps(p.wt, p.wh, p.ww, c);
+  const Taps k = load_taps<T>(p.wt, p.wh, p.ww, c);
   const float mean = q.mean[c], rstd = q.rstd[c], gam = p.gamma[c], bet = p.beta[c];
   const T* base = x + (long long)n * p.T * p.sx.f + c * p.sx.c;
   const T* gb = g + (long long)n * p.T * p.sy.f + c * p.sy.c;
@@ -235,7 +243,7 @@ __global__ void __launch_bounds__(256) gen_bwd_dz(const T* __restrict__ g, const
     }
     return;
   }
-  const Taps k = load_taps(p.wt, p.wh, p.ww, c);
+  const Taps k = load_taps<T>(p.wt, p.wh, p.ww, c);
   const float mean = q.mean[c], rstd = q.rstd[c], gam = p.gamma[c], bet = p.beta[c];
   const double m = (double)p.N * vol;
   const float mdb = p.training ? (float)(q.sums[c] / m) : 0.f;
@@ -256,7 +264,7 @@ template <typename T>
 __global__ void __launch_bounds__(256) gen_bwd_dx(const T* __restrict__ x, T* __restrict__ dx, GenBwdParams q) {
   const GenParams& p = q.f;
   const int c = blockIdx.x, n = blockIdx.y;
-  const Taps k = load_taps(p.wt, p.wh, p.ww, c);
+  const Taps k = load_taps<T>(p.wt, p.wh, p.ww, c);
   const int vol = p.T * p.H * p.W, HW = p.H * p.W;
   const float* dz = q.dz + ((long long)n * p.Cs + c) * vol;
   const T* base = x + (long long)n * p.T * p.sx.f + c * p.sx.c;

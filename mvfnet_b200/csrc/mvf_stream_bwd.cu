@@ -96,7 +96,7 @@ __device__ __forceinline__ void load_coef(float* s_coef, float* scratch, const B
     const int view = i / g.Cg, ch = i - view * g.Cg, c3 = (c0 + ch) * 3;
     const float* wv = view == 0 ? a.wt : (view == 1 ? a.wh : a.ww);
     float w0 = 0.f, w1 = 0.f, w2 = 0.f;
-    if (wv) { w0 = wv[c3]; w1 = wv[c3 + 1]; w2 = wv[c3 + 2]; }
+    if (wv) { w0 = round_bf16(wv[c3]); w1 = round_bf16(wv[c3 + 1]); w2 = round_bf16(wv[c3 + 2]); }
     s_coef[(1 + 2 * view) * g.Cg + ch] = w0;
     s_coef[(2 + 2 * view) * g.Cg + ch] = w2;
     scratch[view * g.Cg + ch] = w1;

@@ -187,6 +187,9 @@ __device__ __forceinline__ uint32_t elect_one() {
 }
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+// bf16 activations imply bf16 stencil taps (the reference's autocast path casts its Conv3d weights): every MVF kernel
+// that takes bf16 tensors rounds each of the nine taps with this before use, forward and backward alike.
+__device__ __forceinline__ float round_bf16(float w) { return __bfloat162float(__float2bfloat16_rn(w)); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
   uint32_t r;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));

@@ -34,6 +34,15 @@ def rel_err_kinks(a, b, max_outliers=8):
     return float(err.max() / max(np.abs(b).max(), 1e-12))
 
 
+def bf16_taps(w):
+    """bf16 storage semantics: kernels that take bf16 activations use bf16 stencil taps (each of the nine taps rounded
+    to bf16, exactly what the reference's autocast path does to its Conv3d weights -- include/mvf_b200.h).  The
+    oracle is evaluated on the same rounded taps so that only the kernels' own arithmetic remains in the comparison."""
+    if w is None:
+        return None
+    return torch.as_tensor(np.asarray(w)).to(torch.bfloat16).double().numpy()
+
+
 def build_mvf(cs_in, t, alpha, mode, share, use_hs, params, rm, rv, training, dev="cuda"):
     from mvfnet_b200 import MVF
     m = MVF(torch.nn.Identity(), t, cs_in, alpha=alpha, use_hs=use_hs, share=share, mode=mode)
@@ -83,7 +92,7 @@ def test_mvf_golden(name, variant):
     else:
         t = int(c["meta"][1])
         kw = dict(mode=str(c["mode"]), share=bool(c["meta"][6]), use_hs=bool(c["meta"][7]), training=bool(c["meta"][8]))
-        tap = lambda k: c[k].reshape(cs, 3) if k in c else None
+        tap = lambda k: bf16_taps(c[k].reshape(cs, 3)) if k in c else None
         w3 = dict(wt=tap("p.shift_conv.weight"), wh=tap("p.h_conv.weight"), ww=tap("p.w_conv.weight"))
         bn = dict(gamma=c.get("p.bn.weight"), beta=c.get("p.bn.bias"), running_mean=c.get("rm"), running_var=c.get("rv"))
         gy = torch.as_tensor(c["gy"]).to(dtype).double().numpy()
@@ -147,7 +156,8 @@ def test_mvf_vs_oracle_model_shapes(C, H, Cs, T, training, dtype):
     xd = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
     y = m(xd)
     y.backward(gy.cuda().contiguous(memory_format=torch.channels_last))
-    tap = lambda p: p.detach().double().cpu().numpy().reshape(Cs, 3)
+    exact = lambda p: p.detach().double().cpu().numpy().reshape(Cs, 3)
+    tap = (lambda p: bf16_taps(exact(p))) if dtype == "bf16" else exact
     kw = dict(wt=tap(m.shift_conv.weight), wh=tap(m.h_conv.weight), ww=tap(m.w_conv.weight),
               gamma=m.bn.weight.detach().double().cpu().numpy(), beta=m.bn.bias.detach().double().cpu().numpy(),
               running_mean=rm0, running_var=rv0, mode="THW", use_hs=True, training=training)
@@ -156,6 +166,9 @@ def test_mvf_vs_oracle_model_shapes(C, H, Cs, T, training, dtype):
     kw.pop("training")
     rb = O.mvf_backward(gs, xs, T, Cs, training=training, **kw)
     assert rel_err(y.detach().double().cpu().numpy(), rf["out"]) < tol
+    if dtype == "bf16":        # and against the reference semantics proper (fp32 taps): still within the bf16 tolerance
+        kx = dict(kw, wt=exact(m.shift_conv.weight), wh=exact(m.h_conv.weight), ww=exact(m.w_conv.weight))
+        assert rel_err(y.detach().double().cpu().numpy(), O.mvf_forward(xs, T, Cs, training=training, **kx)["out"]) < tol
     assert torch.equal(y.detach()[:, Cs:], xd.detach()[:, Cs:])
     assert rel_err_kinks(xd.grad.double().cpu().numpy(), rb["dx"]) < 2 * tol
     gt = 2 * tol if dtype == "f32" else 4 * tol
@@ -198,7 +211,8 @@ def test_mvf_variants_vs_oracle(mode, share, use_hs, dtype, training):
     xd.requires_grad_(True)
     y = m(xd)
     y.backward(gd)
-    tap = lambda name: getattr(m, name).weight.detach().double().cpu().numpy().reshape(Cs, 3) if hasattr(m, name) else None
+    rnd = bf16_taps if dtype == "bf16" else (lambda w: w)
+    tap = lambda name: rnd(getattr(m, name).weight.detach().double().cpu().numpy().reshape(Cs, 3)) if hasattr(m, name) else None
     kw = dict(wt=tap("shift_conv"), wh=tap("h_conv"), ww=tap("w_conv"), gamma=m.bn.weight.detach().double().cpu().numpy(),
               beta=m.bn.bias.detach().double().cpu().numpy(), running_mean=rm0.double().numpy(), running_var=rv0.double().numpy(),
               mode=mode, share=share, use_hs=use_hs)
