@@ -50,6 +50,7 @@ constexpr int kSlotB = 10496;                  // compile-time slot stride: 14x1
 constexpr int kCWarps = 7;                     // consumer warps (+1 producer warp = 2 warps per SM sub-partition)
 constexpr int kMaxItems = 2 * 32 * kCWarps;    // two items per consumer thread
 constexpr int kThreads = 32 * (kCWarps + 1);
+constexpr int kTailB = 8192;                   // BN affine, reduction scratch (<= 64 channels per CTA)
 
 constexpr int MODE_PLAIN = 0;                  // use_hs = False: the stencil only
 constexpr int MODE_EVAL = 1;                   // BN from running statistics + hard-swish
@@ -58,12 +59,15 @@ constexpr int MODE_TRAIN = 2;                  // batch statistics: two sweeps, 
 struct SwGeo {
   int N, T, Cs, H, W;
   int Cg, G, ngroups;     // channels per CTA, 8-channel vectors per pixel, channel groups
-  int hsplit, Hs;         // H tiles and rows per tile
-  int Hp, Wp;             // padded tile extents (Hs+2, W+2)
-  int pixels, pixhalf;    // Hs*W; pixels owned as "item B" start at pixhalf = ceil(pixels/2)
-  int cthreads;           // pixhalf*G consumer threads carry items
+  int hsplit, wsplit;     // H x W tiles per frame
+  int Hs, Ws;             // rows / columns per tile
+  int Hp, Wp;             // padded tile extents (Hs+2, Ws+2)
+  int rowpair;            // 1: warp i owns rows (2i, 2i+1) of the tile, lanes = (column, vector); results leave through
+                          //    one TMA store per warp and frame.  0: items dealt linearly, results stored from registers
+  int pixels, pixhalf;    // rowpair = 0: Hs*Ws; pixels owned as "item B" start at pixhalf = ceil(pixels/2)
+  int cthreads;           // rowpair = 0: pixhalf*G consumer threads carry items
   int cwarps;             // consumer warps (<= kCWarps)
-  int P;                  // CTAs sharing one (channel group, H tile): clips are dealt round-robin
+  int P;                  // CTAs sharing one (channel group, tile): clips are dealt round-robin
 };
 
 struct SwArgs {
@@ -142,12 +146,25 @@ __device__ __forceinline__ void wait_phase(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
+// Non-blocking probe of an mbarrier phase; the result is consumed a whole frame step later.
+__device__ __forceinline__ uint32_t test_phase(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok;
+}
+
 template <int... I, class F>
 __device__ __forceinline__ void static_for(std::integer_sequence<int, I...>, F&& f) {
   (f(std::integral_constant<int, I>{}), ...);
 }
 
-template <int MODE, int TT>
+template <int MODE, int TT, bool RP>
 __global__ void __launch_bounds__(kThreads, 1)
 mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -156,11 +173,12 @@ mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
   const SwGeo& g = a.g;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nconsumer = 32 * g.cwarps;
-  // CTA -> (channel group, H tile, clip lane)
+  // CTA -> (channel group, tile, clip lane)
   const int cg = blockIdx.x % g.ngroups;
   const int rest = blockIdx.x / g.ngroups;
-  const int hs = rest % g.hsplit, p = rest / g.hsplit;
-  const int c0 = cg * g.Cg, h0 = hs * g.Hs;
+  const int ntiles = g.hsplit * g.wsplit;
+  const int tile = rest % ntiles, p = rest / ntiles;
+  const int c0 = cg * g.Cg, h0 = (tile / g.wsplit) * g.Hs, w0 = (tile % g.wsplit) * g.Ws;
   const int nclips = p < g.N ? (g.N - p + g.P - 1) / g.P : 0;
   const int KK = MODE == MODE_TRAIN ? 2 * nclips : nclips;     // clips in this CTA's stream (both sweeps)
 
@@ -175,9 +193,9 @@ mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
 
   const uint32_t frame_bytes = (uint32_t)(g.Hp * g.Wp * g.Cg * 2);
   // item mapping of a consumer thread (the producer warp computes it too and ignores it)
-  const bool actA = tid < g.cthreads;
-  const int it = actA ? tid : 0;                                // spare lanes shadow item 0
-  const int vec = it % g.G, pixA = it / g.G;
+  const bool actA = RP ? lane < g.Ws * g.G : tid < g.cthreads;
+  const int it = actA ? (RP ? lane : tid) : 0;                  // spare lanes shadow item 0
+  const int vec = it % g.G, pixA = it / g.G;                    // rowpair: pixA is the column
   // Stencil taps (and, in eval mode, BatchNorm parameters) of this thread's 8 channels straight from global memory:
   // threads with equal `vec` read the same 96 B per view (L1 broadcast).  Issued FIRST, ahead of the TMA burst that
   // fills the ring, so that they are one uncongested memory round trip hidden behind the first frame.
@@ -227,7 +245,7 @@ mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
       for (int t = 0; t < T; ++t) {
         const int s = kk * T + t;
         mbar_arrive_expect_tx(&full[s], frame_bytes);
-        tma_load_4d(slots + (size_t)s * kSlotB, &tmx, &full[s], c0, -1, h0 - 1, n * T + t);
+        tma_load_4d(slots + (size_t)s * kSlotB, &tmx, &full[s], c0, w0 - 1, h0 - 1, n * T + t);
       }
     }
   }
@@ -247,17 +265,20 @@ mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
           if (MODE == MODE_TRAIN && kk * T + t == nclips * T + a.pre_frames) mbar_wait(gate, 0);
           if (use > 0) mbar_wait(&empty[s], (use - 1) & 1);
           mbar_arrive_expect_tx(&full[s], frame_bytes);
-          tma_load_4d(slots + (size_t)s * kSlotB, &tmx, &full[s], c0, -1, h0 - 1, n * T + t);
+          tma_load_4d(slots + (size_t)s * kSlotB, &tmx, &full[s], c0, w0 - 1, h0 - 1, n * T + t);
         }
         if (++cm == M) { cm = 0; ++use; }
       }
     }
   } else if (nclips > 0) {
-    // ===== consumers: two (pixel, 8-channel vector) items per thread, same channel vector
-    const bool actB = actA && pixA + g.pixhalf < g.pixels;
+    // ===== consumers: two (pixel, 8-channel vector) items per thread, same channel vector.
+    // rowpair: item A = (row 2*warp, column), item B = the pixel below it, so A's lower and B's upper neighbour are
+    // the other item's centre (8 shared-memory loads per frame step instead of 10, all conflict-free: a quarter warp
+    // reads 128 contiguous bytes) and the warp's results are the rectangle rows (2*warp, 2*warp+1) x Ws x Cg.
+    const bool actB = RP ? actA : (actA && pixA + g.pixhalf < g.pixels);
     const int pixB = actB ? pixA + g.pixhalf : pixA;
-    const int hA = pixA / g.W, wA = pixA - hA * g.W;            // row within the H tile, column
-    const int hB = pixB / g.W, wB = pixB - hB * g.W;
+    const int hA = RP ? 2 * warp : pixA / g.Ws, wA = RP ? pixA : pixA - hA * g.Ws;   // row / column within the tile
+    const int hB = RP ? hA + 1 : pixB / g.Ws, wB = RP ? wA : pixB - hB * g.Ws;
     const int pixb = g.Cg * 2, rowb = g.Wp * pixb;
     const uint32_t offA = (uint32_t)(((hA + 1) * g.Wp + (wA + 1)) * pixb + vec * 16);
     const uint32_t offB = (uint32_t)(((hB + 1) * g.Wp + (wB + 1)) * pixb + vec * 16);
@@ -320,8 +341,9 @@ mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
       }
     };
     const size_t frame_elems = (size_t)g.H * g.W * a.y_pix;
-    const size_t ypixA = ((size_t)(h0 + hA) * g.W + wA) * a.y_pix + c0 + vec * 8;
-    const size_t ypixB = ((size_t)(h0 + hB) * g.W + wB) * a.y_pix + c0 + vec * 8;
+    const size_t ypixA = ((size_t)(h0 + hA) * g.W + w0 + wA) * a.y_pix + c0 + vec * 8;
+    const size_t ypixB = ((size_t)(h0 + hB) * g.W + w0 + wB) * a.y_pix + c0 + vec * 8;
+
     const uint32_t full0 = smem_u32(full), slots0 = smem_u32(slots);
 
     float2 sum[4], sq[4];
@@ -334,9 +356,24 @@ mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
     if (stamps && tid == 0) stamps[1] = gtimer();               // prologue done
     wait_phase(full0, 0);
     if (stamps && tid == 0) stamps[2] = gtimer();               // first frame landed
+
+    // Everything a frame step reads from shared memory is loaded ONE STEP AHEAD: step t computes frame t from
+    // registers (centres of t-1, t, t+1 and the H/W neighbours of t) while the loads of slot t+1 (centre of t+1, used
+    // by this step's last tap, and the neighbours of t+1, used by the next step) are in flight, and the barrier of
+    // slot t+2 is TESTED (non-blocking) so that the next step branches on a predicate that is already there.  Neither
+    // the barrier round trip nor the load latency is on the critical path of a step.
+    struct Nb { P8 hm, hp, wm, wp; };                            // rowpair: A uses hm/wm/wp, B uses hp/wm/wp
+    auto load_nb = [&](uint32_t cA, uint32_t cB, Nb& nA, Nb& nB) {
+      nA.hm = lds_p8(cA - rowb); nA.wm = lds_p8(cA - pixb); nA.wp = lds_p8(cA + pixb);
+      nB.hp = lds_p8(cB + rowb); nB.wm = lds_p8(cB - pixb); nB.wp = lds_p8(cB + pixb);
+      if (!RP) { nA.hp = lds_p8(cA + rowb); nB.hm = lds_p8(cB - rowb); }
+    };
     P8 xcA = lds_p8(slots0 + offA), xcB = lds_p8(slots0 + offB), xmA, xmB;   // centre of the first frame
+    Nb nA, nB;
+    load_nb(slots0 + offA, slots0 + offB, nA, nB);
 #pragma unroll
     for (int j = 0; j < 4; ++j) { xmA.v[j] = 0u; xmB.v[j] = 0u; }
+    uint32_t ready = test_phase(full0 + 8u, 0);                 // slot 1 (T >= 4: same slot group, same parity)
 
     // one sweep over the CTA's clips; `stats` is a compile-time tag so that the statistics accumulators (sweep 0)
     // and the BatchNorm affine (sweep 1) never hold registers at the same time
@@ -352,41 +389,47 @@ mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
         const uint32_t cbn = slots0 + (uint32_t)cmn * (uint32_t)(T * kSlotB);
         const uint32_t fulln = full0 + (uint32_t)cmn * (uint32_t)(T * 8);
         const bool has_next = --left > 0;
-        // the five addresses of each item in slot 0 of this clip; frame t adds the compile-time t*kSlotB
-        const uint32_t aC = cb + offA, aHm = aC - rowb, aHp = aC + rowb, aWm = aC - pixb, aWp = aC + pixb;
-        const uint32_t bC = cb + offB, bHm = bC - rowb, bHp = bC + rowb, bWm = bC - pixb, bWp = bC + pixb;
+        const uint32_t aC = cb + offA, bC = cb + offB;          // centres in slot 0 of this clip; frame t adds t*kSlotB
+        const uint32_t aN = cbn + offA, bN = cbn + offB;        // ... and of the next clip
         __nv_bfloat16* ypA = a.y + (size_t)(p + kclip * g.P) * T * frame_elems + ypixA;
         __nv_bfloat16* ypB = a.y + (size_t)(p + kclip * g.P) * T * frame_elems + ypixB;
         static_for(std::make_integer_sequence<int, T>{}, [&](auto tc) {
           constexpr int t = decltype(tc)::value;
-          constexpr uint32_t so = (uint32_t)(t * kSlotB);
-          // H/W neighbours of frame t: its slot is complete, no barrier needed
-          const P8 hmA = lds_p8(aHm + so), hpA = lds_p8(aHp + so), wmA = lds_p8(aWm + so), wpA = lds_p8(aWp + so);
-          const P8 hmB = lds_p8(bHm + so), hpB = lds_p8(bHp + so), wmB = lds_p8(bWm + so), wpB = lds_p8(bWp + so);
+          // (a) slot of frame t+1: its barrier was tested a step ago; load its centre and neighbours
           P8 xnA, xnB;
+          Nb mA = nA, mB = nB;
 #pragma unroll
           for (int j = 0; j < 4; ++j) { xnA.v[j] = 0u; xnB.v[j] = 0u; }
-          if (t + 1 < T) {                                      // centre of the next frame of this clip
-            wait_phase(fullc + 8u * (t + 1), par);
-            xnA = lds_p8(aC + so + kSlotB);
-            xnB = lds_p8(bC + so + kSlotB);
-          } else if (has_next) {                                // ... or of the next clip's first frame
-            wait_phase(fulln, parn);
-            xnA = lds_p8(cbn + offA);
-            xnB = lds_p8(cbn + offB);
+          if (t + 1 < T) {
+            if (!ready) wait_phase(fullc + 8u * (t + 1), par);
+            xnA = lds_p8(aC + (uint32_t)((t + 1) * kSlotB));
+            xnB = lds_p8(bC + (uint32_t)((t + 1) * kSlotB));
+            load_nb(aC + (uint32_t)((t + 1) * kSlotB), bC + (uint32_t)((t + 1) * kSlotB), mA, mB);
+          } else if (has_next) {                                // the next clip's first frame
+            if (!ready) wait_phase(fulln, parn);
+            xnA = lds_p8(aN);
+            xnB = lds_p8(bN);
+            load_nb(aN, bN, mA, mB);
           }
+          // (b) test the barrier of frame t+2's slot for the next step
+          if (t + 2 < T) ready = test_phase(fullc + 8u * (t + 2), par);
+          else if (has_next) ready = test_phase(fulln + 8u * (t + 2 - T), parn);
+          // (c) frame t from registers
+          const P8& hpA = RP ? xcB : nA.hp;
+          const P8& hmB = RP ? xcA : nB.hm;
           float2 zA[4], zB[4];
 #pragma unroll
           for (int j = 0; j < 4; ++j) { fh2_first(zA[j], xcA.v[j], kc.v[j]); fh2_first(zB[j], xcB.v[j], kc.v[j]); }
           fh8(zA, xcA, kcl); fh8(zB, xcB, kcl);
-          fh8(zA, hmA, kh0); fh8(zB, hmB, kh0);
-          fh8(zA, hpA, kh2); fh8(zB, hpB, kh2);
-          fh8(zA, wmA, kw0); fh8(zB, wmB, kw0);
-          fh8(zA, wpA, kw2); fh8(zB, wpB, kw2);
+          fh8(zA, nA.hm, kh0); fh8(zB, hmB, kh0);
+          fh8(zA, hpA, kh2); fh8(zB, nB.hp, kh2);
+          fh8(zA, nA.wm, kw0); fh8(zB, nB.wm, kw0);
+          fh8(zA, nA.wp, kw2); fh8(zB, nB.wp, kw2);
           if (t > 0) { fh8(zA, xmA, kt0); fh8(zB, xmB, kt0); }  // zero padding in T: the clip's first / last frame
           if (t + 1 < T) { fh8(zA, xnA, kt2); fh8(zB, xnB, kt2); }
+          // (d) frame t's slot was last read a step ago (its values have just been consumed): release it
           __syncwarp();
-          if (lane == 0) arrive_u32(fullc + 8u * kRing + 8u * t);   // this warp is done with frame t's slot
+          if (lane == 0) arrive_u32(fullc + 8u * kRing + 8u * t);
           if (stats) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -415,8 +458,8 @@ mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
             if (actA) *reinterpret_cast<uint4*>(ypA + (size_t)t * frame_elems) = oA;
             if (actB) *reinterpret_cast<uint4*>(ypB + (size_t)t * frame_elems) = oB;
           }
-          xmA = xcA; xcA = xnA;
-          xmB = xcB; xcB = xnB;
+          xmA = xcA; xcA = xnA; nA = mA;
+          xmB = xcB; xcB = xnB; nB = mB;
         });
         cm = cmn;
         par = parn;
@@ -447,7 +490,7 @@ mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
       // Grid-wide exchange without a flag: every partial travels as an 8-byte {value, epoch} word (single-copy
       // atomic), readers poll the words themselves until they carry this launch's epoch.  One store propagation plus
       // one load round trip after the last CTA arrives -- no fence, no atomic counter, no second round of loads.
-      const int per = 2 * g.Cg, rows = g.hsplit * g.P;          // partial rows of this channel group
+      const int per = 2 * g.Cg, rows = ntiles * g.P;               // partial rows of this channel group
       if (tid < per) {                                          // row layout [vec][sum 0..7 | sumsq 0..7]
         float v = 0.f;
         for (int wv = 0; wv < g.cwarps; ++wv) v += s_red[wv * per + tid];
@@ -520,13 +563,71 @@ mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
 }
 
 size_t sweep_smem(const SwGeo& g) {
-  return 384 + (size_t)kRing * kSlotB + (size_t)2 * g.Cg * 4 + (size_t)kThreads * 8 + (size_t)kCWarps * 2 * g.Cg * 4 + 64;
+  return 384 + (size_t)kRing * kSlotB + kTailB + 64;
+}
+
+void finish_geo(const mvfb_mvf_desc* d, SwGeo& g) {
+  g.N = d->N; g.T = d->T; g.Cs = d->Cs; g.H = d->H; g.W = d->W;
+  g.G = g.Cg / 8; g.ngroups = d->Cs / g.Cg;
+  g.Hs = d->H / g.hsplit; g.Ws = d->W / g.wsplit; g.Hp = g.Hs + 2; g.Wp = g.Ws + 2;
+  g.pixels = g.Hs * g.Ws; g.pixhalf = (g.pixels + 1) / 2;
+  if (g.rowpair) {
+    g.cwarps = g.Hs / 2;
+    g.cthreads = 32 * g.cwarps;
+  } else {
+    g.cthreads = g.pixhalf * g.G;
+    g.cwarps = (g.cthreads + 31) / 32;
+  }
+  const int lanes = g.ngroups * g.hsplit * g.wsplit;
+  int P = num_sms() / lanes;
+  if (P < 1) P = 1;
+  if (P > d->N) P = d->N;
+  g.P = P;
 }
 
 bool choose_sweep(const mvfb_mvf_desc* d, SwGeo& g) {
   if (d->dtype != MVFB_BF16 || d->layout != MVFB_NHWC) return false;
   if (d->T != 4 && d->T != 8 && d->T != 16) return false;
-  if (d->Cs % 8 != 0 || d->C % 8 != 0 || d->W + 2 > 256) return false;
+  if (d->Cs % 8 != 0 || d->C % 8 != 0) return false;
+  static const bool no_rowpair = getenv("MVFB_SWEEP_RP") && getenv("MVFB_SWEEP_RP")[0] == '0';   // tuning experiments
+  // 1) row-pair tiles: an even number of rows (one warp per pair, <= kCWarps) and a row of (column, vector) lanes
+  //    that fits a warp.  Wide channel groups first: the TMA unit retires ~1 box row per 1.5 clocks whatever the
+  //    row's size, so 64-byte rows (32 channels) halve its load per element against 32-byte rows (measured: a
+  //    14x14x16-channel frame takes 0.205 us of TMA time, as long as its arithmetic).  Within a width take the
+  //    tiling that loads the fewest halo pixels and idles the fewest lanes.
+  static const int only_cg = getenv("MVFB_SWEEP_CG") ? atoi(getenv("MVFB_SWEEP_CG")) : 0;                // tuning experiments
+  const int cands_rp[2] = {32, 16};
+  for (int ci = 0; ci < 2 && !no_rowpair; ++ci) {
+    const int Cg = cands_rp[ci];
+    if (d->Cs % Cg || (only_cg && Cg != only_cg)) continue;
+    double best = 1e30;
+    SwGeo bg;
+    for (int hsplit = 1; hsplit <= d->H; ++hsplit) {
+      if (d->H % hsplit) continue;
+      const int Hs = d->H / hsplit;
+      if (Hs % 2 || Hs / 2 > kCWarps || 2 * Cg > 32 * (Hs / 2)) continue;
+      for (int wsplit = 1; wsplit <= d->W; ++wsplit) {
+        if (d->W % wsplit) continue;
+        const int Ws = d->W / wsplit;
+        if (Ws * (Cg / 8) > 32 || Ws < 4) continue;
+        if ((Hs + 2) * (Ws + 2) * Cg * 2 > kSlotB) continue;
+        const double halo = (double)((Hs + (hsplit > 1 ? 2 : 0)) * (Ws + (wsplit > 1 ? 2 : 0))) / (Hs * Ws);
+        const double idle = 32.0 / (Ws * (Cg / 8)) * ((double)kCWarps / (Hs / 2) > 2.0 ? 1.5 : 1.0);
+        const double cost = halo * idle;
+        if (cost < best) {
+          best = cost;
+          bg.Cg = Cg; bg.hsplit = hsplit; bg.wsplit = wsplit; bg.rowpair = 1;
+        }
+      }
+    }
+    if (best < 1.8) {
+      g = bg;
+      finish_geo(d, g);
+      if (sweep_smem(g) <= (size_t)kSmemLimit) return true;
+    }
+  }
+  // 2) linear items (odd extents, wide channel groups): H tiles only
+  if (d->W + 2 > 256) return false;
   const int splits[4] = {1, 2, 4, 7};
   const int cands[4] = {64, 32, 16, 8};
   for (int pass = 0; pass < 2; ++pass) {                     // first pass: >= 32-byte rows per pixel only
@@ -539,24 +640,13 @@ bool choose_sweep(const mvfb_mvf_desc* d, SwGeo& g) {
         const int Cg = cands[ci];
         if ((pass == 0) != (Cg >= 16)) continue;
         if (d->Cs % Cg) continue;
-        const int G = Cg / 8;
         const int pixels = Hs * d->W;
-        if (pixels * G > kMaxItems) continue;
-        const int pixhalf = (pixels + 1) / 2;
-        const int cthreads = pixhalf * G;
-        if (cthreads > 32 * kCWarps) continue;
-        const int cwarps = (cthreads + 31) / 32;
-        if (2 * Cg > 32 * cwarps) continue;                  // the statistics reduction needs 2*Cg consumer threads
+        if (pixels * (Cg / 8) > kMaxItems) continue;
+        if (((pixels + 1) / 2) * (Cg / 8) > 32 * kCWarps) continue;
         if ((Hs + 2) * (d->W + 2) * Cg * 2 > kSlotB) continue;
-        g.N = d->N; g.T = d->T; g.Cs = d->Cs; g.H = d->H; g.W = d->W;
-        g.Cg = Cg; g.G = G; g.ngroups = d->Cs / Cg;
-        g.hsplit = hsplit; g.Hs = Hs; g.Hp = Hs + 2; g.Wp = d->W + 2;
-        g.pixels = pixels; g.pixhalf = pixhalf; g.cthreads = cthreads; g.cwarps = cwarps;
-        const int lanes = g.ngroups * hsplit;
-        int P = num_sms() / lanes;
-        if (P < 1) P = 1;
-        if (P > d->N) P = d->N;
-        g.P = P;
+        g.Cg = Cg; g.hsplit = hsplit; g.wsplit = 1; g.rowpair = 0;
+        finish_geo(d, g);
+        if (2 * Cg > 32 * g.cwarps) continue;                // the statistics reduction needs 2*Cg consumer threads
         if (sweep_smem(g) > (size_t)kSmemLimit) continue;
         return true;
       }
@@ -572,39 +662,48 @@ unsigned int next_epoch() {
   return e.fetch_add(1u, std::memory_order_relaxed);
 }
 
-template <int MODE, int TT>
+template <int MODE, int TT, bool RP>
 int launch_mode(const CUtensorMap& tmx, SwArgs& a, cudaStream_t st) {
   static bool once = false;
   if (!once) {
-    MVFB_CUDA(cudaFuncSetAttribute(mvf_sweep_kernel<MODE, TT>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
+    MVFB_CUDA(cudaFuncSetAttribute(mvf_sweep_kernel<MODE, TT, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     once = true;
   }
   const SwGeo& g = a.g;
-  const dim3 grid(g.ngroups * g.hsplit * g.P), block(32 * (g.cwarps + 1));
+  const dim3 grid(g.ngroups * g.hsplit * g.wsplit * g.P), block(32 * (g.cwarps + 1));
   const size_t smem = sweep_smem(g);
   if (MODE == MODE_TRAIN) {
     a.epoch = next_epoch();
     void* params[2] = {(void*)&tmx, (void*)&a};
-    // cooperative launch: the driver guarantees that all CTAs are resident, which the grid barrier relies on
-    cudaError_t e = cudaLaunchCooperativeKernel((const void*)mvf_sweep_kernel<MODE, TT>, grid, block, params, smem, st);
+    // cooperative launch: the driver guarantees that all CTAs are resident, which the grid exchange relies on
+    cudaError_t e = cudaLaunchCooperativeKernel((const void*)mvf_sweep_kernel<MODE, TT, RP>, grid, block, params, smem, st);
     if (e == cudaErrorCooperativeLaunchTooLarge) {
       (void)cudaGetLastError();
       return MVFB_ERR_UNSUPPORTED;                           // device shared with another context: two-launch path
     }
     MVFB_CUDA(e);
   } else {
-    mvf_sweep_kernel<MODE, TT><<<grid, block, smem, st>>>(tmx, a);
+    mvf_sweep_kernel<MODE, TT, RP><<<grid, block, smem, st>>>(tmx, a);
   }
   count_launch();
   MVFB_LAUNCH_CHECK();
   return MVFB_OK;
 }
 
-template <int TT>
+template <int TT, bool RP>
 int launch_sweep(const mvfb_mvf_desc* d, const CUtensorMap& tmx, SwArgs& a, cudaStream_t st) {
-  if (!d->use_hs) return launch_mode<MODE_PLAIN, TT>(tmx, a, st);
-  if (d->training) return launch_mode<MODE_TRAIN, TT>(tmx, a, st);
-  return launch_mode<MODE_EVAL, TT>(tmx, a, st);
+  if (!d->use_hs) return launch_mode<MODE_PLAIN, TT, RP>(tmx, a, st);
+  if (d->training) return launch_mode<MODE_TRAIN, TT, RP>(tmx, a, st);
+  return launch_mode<MODE_EVAL, TT, RP>(tmx, a, st);
+}
+
+template <bool RP>
+int launch_T(const mvfb_mvf_desc* d, const CUtensorMap& tmx, SwArgs& a, cudaStream_t st) {
+  switch (a.g.T) {
+    case 4: return launch_sweep<4, RP>(d, tmx, a, st);
+    case 8: return launch_sweep<8, RP>(d, tmx, a, st);
+    default: return launch_sweep<16, RP>(d, tmx, a, st);
+  }
 }
 
 }  // namespace
@@ -617,7 +716,7 @@ bool mvf_sweep_supported(const mvfb_mvf_desc* d) {
 size_t mvf_sweep_ws(const mvfb_mvf_desc* d) {
   SwGeo g;
   if (!choose_sweep(d, g)) return 0;
-  return (size_t)g.ngroups * g.hsplit * g.P * 2 * g.Cg * sizeof(uint2) + 256;
+  return (size_t)g.ngroups * g.hsplit * g.wsplit * g.P * 2 * g.Cg * sizeof(uint2) + 256;
 }
 
 int mvf_sweep_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_stride, const float* wt,
@@ -650,11 +749,7 @@ int mvf_sweep_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_st
   a.y = (__nv_bfloat16*)y; a.y_pix = y_stride;
   static const bool debug = getenv("MVFB_SWEEP_DEBUG") != nullptr;       // the tool passes a 1 MiB workspace
   a.stamps = debug ? reinterpret_cast<unsigned long long*>((char*)ws + (512 << 10)) : nullptr;
-  switch (g.T) {
-    case 4: return launch_sweep<4>(d, tmx, a, st);
-    case 8: return launch_sweep<8>(d, tmx, a, st);
-    default: return launch_sweep<16>(d, tmx, a, st);
-  }
+  return g.rowpair ? launch_T<true>(d, tmx, a, st) : launch_T<false>(d, tmx, a, st);
 }
 
 }  // namespace mvfb
