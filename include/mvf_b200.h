@@ -189,6 +189,24 @@ int bn_bwd(const mvfb_bn_desc* d, const void* g, long long ldg, const void* y, l
            void* dres, long long lddr, float* dgamma, float* dbeta, float* sums, const unsigned char* relu_mask,
            mvfb_stream_t stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * ResNet stem  --  replaces conv1 = nn.Conv2d(3, 64, 7, stride 2, padding 3, bias=False) and
+ * maxpool = nn.MaxPool2d(3, 2, 1) of ResNet.forward (backbones/resnet.py:424-431, 481-484).
+ *
+ *   stem_im2col      : x (F, H, W, 3) bf16 NHWC -> a (F*Ho*Wo, 192) bf16 row-major, Ho = (H-1)/2+1: the 7x7x3
+ *                      patch of every output pixel, K ordered (kh, kw, c), zero padded from 147 to 192 columns.
+ *                      conv1x1_gemm(a, W (64,192)) is then the convolution (BatchNorm sums in its epilogue) and
+ *                      conv1x1_wgrad(dY, a) its weight gradient.
+ *   maxpool3x3s2_fwd : x (F, H, W, C) bf16 NHWC -> y (F, Ho, Wo, C) and idx (F, Ho, Wo, C) bytes = position of the
+ *                      maximum inside the 3x3 window (kh*3 + kw; the first maximum in scan order, NaN wins: the
+ *                      rule of ATen's max_pool2d kernels).  C % 8 == 0.
+ *   maxpool3x3s2_bwd : dx (F, H, W, C) = g (F, Ho, Wo, C) routed to the recorded positions (gather over the <= 4
+ *                      windows containing a pixel; every element of dx is written).
+ * ---------------------------------------------------------------------------------------------- */
+int stem_im2col(const void* x, void* a, long long F, int H, int W, mvfb_stream_t stream);
+int maxpool3x3s2_fwd(const void* x, void* y, void* idx, long long F, int H, int W, int C, mvfb_stream_t stream);
+int maxpool3x3s2_bwd(const void* g, const void* idx, void* dx, long long F, int H, int W, int C, mvfb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

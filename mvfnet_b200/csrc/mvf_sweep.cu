@@ -194,7 +194,11 @@ mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
   const uint32_t frame_bytes = (uint32_t)(g.Hp * g.Wp * g.Cg * 2);
   // item mapping of a consumer thread (the producer warp computes it too and ignores it)
   const bool actA = RP ? lane < g.Ws * g.G : tid < g.cthreads;
-  const int it = actA ? (RP ? lane : tid) : 0;                  // spare lanes shadow item 0
+  // spare lanes shadow an active lane of their own quarter warp (same address: a broadcast, not a bank conflict)
+  int it = RP ? lane : tid;
+  if (!actA) {
+    if (RP) { while (it >= g.Ws * g.G) it -= g.G; } else { it = 0; }
+  }
   const int vec = it % g.G, pixA = it / g.G;                    // rowpair: pixA is the column
   // Stencil taps (and, in eval mode, BatchNorm parameters) of this thread's 8 channels straight from global memory:
   // threads with equal `vec` read the same 96 B per view (L1 broadcast).  Issued FIRST, ahead of the TMA burst that

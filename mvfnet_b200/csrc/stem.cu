@@ -1,0 +1,202 @@
+// ResNet stem (backbones/resnet.py:424-431, 481-484): Conv2d(3, 64, 7, stride 2, pad 3) and MaxPool2d(3, 2, 1).
+//
+// The step's launch list (profiles/r01_step_launches_final.txt) had the cuDNN stem convolution at 9.6 % of the step
+// (one launch, 11 ms for 1024 frames: 3 input channels do not feed an implicit-GEMM kernel), its weight gradient at
+// 2.6 % and ATen's max-pool pair at 8.9 %.  Here:
+//   * stem_im2col: the 7x7x3 patches of every output pixel as rows of a (F*Ho*Wo, 192) bf16 matrix, K ordered
+//     (kh, kw, c) -- in an NHWC image with 3 channels the 21 values of one kernel row are 21 CONTIGUOUS elements --
+//     zero padded from 147 to 192 so that the tcgen05 GEMMs of this library take it as a 1x1 convolution:
+//     conv1x1_gemm gives the convolution (with the BatchNorm statistics in its epilogue), conv1x1_wgrad its
+//     weight gradient.  The input needs no gradient.
+//   * maxpool3x3s2_fwd / _bwd: NHWC bf16, 8 channels per thread; the forward records the arg-max position inside the
+//     window (0..8, one byte per element, first maximum in (kh, kw) scan order exactly as ATen's kernels), the
+//     backward GATHERS: every input pixel looks at the <= 4 windows that contain it.  No atomics, no int64 indices.
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "common.cuh"
+#include "mvf_internal.cuh"
+#include "ptx.cuh"
+
+namespace mvfb {
+
+namespace {
+
+constexpr int kStemK = 147, kStemKp = 192;
+
+// x: (F, H, W, 3) bf16 NHWC.  One thread per (output pixel, 8-element chunk of the 192-wide row).
+__global__ void __launch_bounds__(256)
+stem_im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ a, int H, int W, int Ho, int Wo,
+                   long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int chunk = (int)(i % (kStemKp / 8));
+  const long long row = i / (kStemKp / 8);
+  const int ow = (int)(row % Wo);
+  const long long t = row / Wo;
+  const int oh = (int)(t % Ho);
+  const long long f = t / Ho;
+  const int rowlen = W * 3;
+  const int e0 = (2 * ow - 3) * 3;                              // element offset of kw = 0, c = 0 inside an image row
+  const unsigned short* img = reinterpret_cast<const unsigned short*>(x) + f * (long long)H * rowlen;
+  unsigned short v[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) {
+    const int k = chunk * 8 + e;
+    const int kh = k / 21, r = k - kh * 21;                     // k = (kh*7 + kw)*3 + c
+    const int ih = 2 * oh - 3 + kh, off = e0 + r;
+    unsigned short val = 0;
+    if (k < kStemK && ih >= 0 && ih < H && off >= 0 && off < rowlen) val = __ldg(img + (long long)ih * rowlen + off);
+    v[e] = val;
+  }
+  uint4 o;
+  o.x = v[0] | ((uint32_t)v[1] << 16); o.y = v[2] | ((uint32_t)v[3] << 16);
+  o.z = v[4] | ((uint32_t)v[5] << 16); o.w = v[6] | ((uint32_t)v[7] << 16);
+  reinterpret_cast<uint4*>(a)[i] = o;
+}
+
+__device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+
+// x: (F, H, W, C) bf16 NHWC -> y: (F, Ho, Wo, C), idx: (F, Ho, Wo, C) bytes.  One thread per (output pixel, 8 channels).
+__global__ void __launch_bounds__(256)
+maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint2* __restrict__ idx, int H, int W, int Ho,
+                   int Wo, int C8, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % C8);
+  long long t = i / C8;
+  const int ow = (int)(t % Wo); t /= Wo;
+  const int oh = (int)(t % Ho);
+  const long long f = t / Ho;
+  float best[8];
+  int arg[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; arg[e] = 0; }
+  bool any = false;
+#pragma unroll
+  for (int kh = 0; kh < 3; ++kh) {
+    const int ih = 2 * oh - 1 + kh;
+    if (ih < 0 || ih >= H) continue;
+#pragma unroll
+    for (int kw = 0; kw < 3; ++kw) {
+      const int iw = 2 * ow - 1 + kw;
+      if (iw < 0 || iw >= W) continue;
+      const uint4 v = __ldg(x + ((f * H + ih) * W + iw) * C8 + c8);
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float lo = bf_lo(w4[q]), hi = bf_hi(w4[q]);
+        // ATen: (val > maxval) || isnan(val); the first valid element always replaces -inf
+        if (!any || lo > best[2 * q] || lo != lo) { best[2 * q] = lo; arg[2 * q] = kh * 3 + kw; }
+        if (!any || hi > best[2 * q + 1] || hi != hi) { best[2 * q + 1] = hi; arg[2 * q + 1] = kh * 3 + kw; }
+      }
+      any = true;
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16(best[0], best[1]); o.y = pack_bf16(best[2], best[3]);
+  o.z = pack_bf16(best[4], best[5]); o.w = pack_bf16(best[6], best[7]);
+  y[i] = o;
+  uint2 k;
+  k.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
+  k.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+  idx[i] = k;
+}
+
+// dx[f, ih, iw, c] = sum over the windows (oh, ow) that contain (ih, iw) of g[f, oh, ow, c] * [idx[f, oh, ow, c] == position]
+__global__ void __launch_bounds__(256)
+maxpool_bwd_kernel(const uint4* __restrict__ g, const uint2* __restrict__ idx, uint4* __restrict__ dx, int H, int W,
+                   int Ho, int Wo, int C8, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c8 = (int)(i % C8);
+  long long t = i / C8;
+  const int iw = (int)(t % W); t /= W;
+  const int ih = (int)(t % H);
+  const long long f = t / H;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  // windows: 2*oh - 1 <= ih <= 2*oh + 1
+  const int oh0 = ih >> 1, oh1 = (ih + 1) >> 1;                 // equal when ih is even ... (ih odd: two windows)
+  const int ow0 = iw >> 1, ow1 = (iw + 1) >> 1;
+#pragma unroll
+  for (int a = 0; a < 2; ++a) {
+    const int oh = a == 0 ? oh0 : oh1;
+    if (a == 1 && oh1 == oh0) continue;
+    if (oh >= Ho) continue;
+    const int kh = ih - (2 * oh - 1);
+#pragma unroll
+    for (int b = 0; b < 2; ++b) {
+      const int ow = b == 0 ? ow0 : ow1;
+      if (b == 1 && ow1 == ow0) continue;
+      if (ow >= Wo) continue;
+      const int pos = kh * 3 + (iw - (2 * ow - 1));
+      const long long o = ((f * Ho + oh) * Wo + ow) * C8 + c8;
+      const uint2 k = __ldg(idx + o);
+      const uint4 v = __ldg(g + o);
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t kk = q < 2 ? k.x : k.y;
+        const int sh = (q & 1) * 16;
+        if ((int)((kk >> sh) & 0xff) == pos) acc[2 * q] += bf_lo(w4[q]);
+        if ((int)((kk >> (sh + 8)) & 0xff) == pos) acc[2 * q + 1] += bf_hi(w4[q]);
+      }
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+  o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+  dx[i] = o;
+}
+
+}  // namespace
+
+}  // namespace mvfb
+
+using namespace mvfb;
+
+extern "C" {
+
+int stem_im2col(const void* x, void* a, long long F, int H, int W, mvfb_stream_t stream) {
+  MVFB_CHECK(x && a && F > 0 && H > 0 && W > 0, MVFB_ERR_ARG, "stem_im2col: bad arguments");
+  MVFB_CHECK(!(reinterpret_cast<uintptr_t>(a) & 15), MVFB_ERR_ARG, "stem_im2col: output must be 16-byte aligned");
+  const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
+  const long long total = F * Ho * Wo * (kStemKp / 8);
+  const unsigned blocks = (unsigned)ceil_div_ll(total, 256);
+  stem_im2col_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)a, H, W, Ho, Wo,
+                                                                total);
+  count_launch();
+  MVFB_LAUNCH_CHECK();
+  return MVFB_OK;
+}
+
+int maxpool3x3s2_fwd(const void* x, void* y, void* idx, long long F, int H, int W, int C, mvfb_stream_t stream) {
+  MVFB_CHECK(x && y && idx && F > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, MVFB_ERR_ARG, "maxpool3x3s2_fwd: bad arguments");
+  MVFB_CHECK(!((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) && !(reinterpret_cast<uintptr_t>(idx) & 7),
+             MVFB_ERR_ARG, "maxpool3x3s2_fwd: misaligned tensors");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = F * Ho * Wo * (C / 8);
+  maxpool_fwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)x, (uint4*)y, (uint2*)idx, H, W, Ho, Wo, C / 8, total);
+  count_launch();
+  MVFB_LAUNCH_CHECK();
+  return MVFB_OK;
+}
+
+int maxpool3x3s2_bwd(const void* g, const void* idx, void* dx, long long F, int H, int W, int C, mvfb_stream_t stream) {
+  MVFB_CHECK(g && dx && idx && F > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, MVFB_ERR_ARG, "maxpool3x3s2_bwd: bad arguments");
+  MVFB_CHECK(!((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(dx)) & 15) && !(reinterpret_cast<uintptr_t>(idx) & 7),
+             MVFB_ERR_ARG, "maxpool3x3s2_bwd: misaligned tensors");
+  const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  const long long total = F * H * W * (C / 8);
+  maxpool_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(
+      (const uint4*)g, (const uint2*)idx, (uint4*)dx, H, W, Ho, Wo, C / 8, total);
+  count_launch();
+  MVFB_LAUNCH_CHECK();
+  return MVFB_OK;
+}
+
+}  // extern "C"

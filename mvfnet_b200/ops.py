@@ -59,6 +59,12 @@ def _L():
         L.bn_bwd.restype = C.c_int
         L.bn_bwd.argtypes = [C.POINTER(BnDesc), _VP, _LL, _VP, _LL, _VP, _LL, _VP, _VP, _VP, _VP, _LL, _VP, _LL, _VP,
                              _VP, _VP, _VP, _VP]
+        L.stem_im2col.restype = C.c_int
+        L.stem_im2col.argtypes = [_VP, _VP, _LL, C.c_int, C.c_int, _VP]
+        L.maxpool3x3s2_fwd.restype = C.c_int
+        L.maxpool3x3s2_fwd.argtypes = [_VP, _VP, _VP, _LL, C.c_int, C.c_int, C.c_int, _VP]
+        L.maxpool3x3s2_bwd.restype = C.c_int
+        L.maxpool3x3s2_bwd.argtypes = [_VP, _VP, _VP, _LL, C.c_int, C.c_int, C.c_int, _VP]
         _declared = True
     return L
 
@@ -350,6 +356,101 @@ def conv3x3(x, weight, stride=1, stats=False):
 
 
 # ------------------------------------------------------------------------------------------------ BatchNorm
+# ---------------------------------------------------------------------------------------------- stem
+STEM_K, STEM_KP = 147, 192
+
+
+def stem_enabled() -> bool:
+    """MVFB_STEM=0 routes the stem convolution and max-pool back through torch / cuDNN (A/B measurements only)."""
+    return os.environ.get("MVFB_STEM", "1") != "0"
+
+
+def stem_eligible(x, conv) -> bool:
+    """ResNet.conv1 (3 -> 64, 7x7, stride 2, pad 3, no bias) in the bf16 configuration; the input needs no gradient."""
+    bf16 = x.dtype == torch.bfloat16 or (torch.is_autocast_enabled() and torch.get_autocast_dtype('cuda') == torch.bfloat16)
+    return (stem_enabled() and x.is_cuda and bf16 and x.dim() == 4 and x.shape[1] == 3 and not x.requires_grad
+            and type(conv) is torch.nn.Conv2d and conv.in_channels == 3 and conv.out_channels == 64
+            and conv.kernel_size == (7, 7) and conv.stride == (2, 2) and conv.padding == (3, 3) and conv.bias is None
+            and conv.groups == 1 and conv.dilation == (1, 1))
+
+
+class _StemConv(torch.autograd.Function):
+    """conv1 of the ResNet stem as im2col (stem_im2col) + the tcgen05 GEMMs (backbones/resnet.py:424, 481)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stats):
+        L = _L()
+        f, _, h, w = x.shape
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        xb = x.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)   # (F, H, W, 3) in memory
+        a = torch.empty((f * ho * wo, STEM_KP), dtype=torch.bfloat16, device=x.device)
+        _lib.check(L.stem_im2col(ptr(xb), ptr(a), f, h, w, _stream()), "stem_im2col")
+        wm = torch.zeros((64, STEM_KP), dtype=torch.bfloat16, device=x.device)
+        wm[:, :STEM_K] = weight.detach().permute(0, 2, 3, 1).reshape(64, STEM_K)           # K order (kh, kw, c)
+        out, colsum, _ = gemm_tn(a, wm, stats=stats)
+        ctx.save_for_backward(a)
+        ctx.wdtype = weight.dtype
+        y = _nhwc_from_rows(out, f, ho, wo)
+        if not stats:
+            return y
+        sums = colsum._base if colsum._base is not None else colsum
+        ctx.mark_non_differentiable(sums)
+        return y, sums
+
+    @staticmethod
+    def backward(ctx, g, *unused):
+        (a,) = ctx.saved_tensors
+        dw = None
+        if ctx.needs_input_grad[1]:
+            g2 = _rows(g.contiguous(memory_format=torch.channels_last))
+            dw = gemm_wgrad(g2, a)[:, :STEM_K].reshape(64, 7, 7, 3).permute(0, 3, 1, 2).to(ctx.wdtype)
+        return None, dw, None
+
+
+def stem_conv(x, weight, stats=False):
+    return _StemConv.apply(x, weight, stats)
+
+
+def maxpool_eligible(x, pool) -> bool:
+    ks = pool.kernel_size if isinstance(pool.kernel_size, tuple) else (pool.kernel_size,) * 2
+    st = pool.stride if isinstance(pool.stride, tuple) else (pool.stride,) * 2
+    pd = pool.padding if isinstance(pool.padding, tuple) else (pool.padding,) * 2
+    dl = pool.dilation if isinstance(pool.dilation, tuple) else (pool.dilation,) * 2
+    return (stem_enabled() and x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4 and x.shape[1] % 8 == 0
+            and x.is_contiguous(memory_format=torch.channels_last) and ks == (3, 3) and st == (2, 2) and pd == (1, 1)
+            and dl == (1, 1) and not pool.ceil_mode and not pool.return_indices)
+
+
+class _MaxPool3x3s2(torch.autograd.Function):
+    """nn.MaxPool2d(3, 2, 1) on bf16 channels_last tensors; one byte of arg-max per output element."""
+
+    @staticmethod
+    def forward(ctx, x):
+        L = _L()
+        f, c, h, w = x.shape
+        ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+        y = torch.empty((f, ho, wo, c), dtype=torch.bfloat16, device=x.device)
+        idx = torch.empty((f, ho, wo, c), dtype=torch.uint8, device=x.device)
+        _lib.check(L.maxpool3x3s2_fwd(ptr(x), ptr(y), ptr(idx), f, h, w, c, _stream()), "maxpool3x3s2_fwd")
+        ctx.save_for_backward(idx)
+        ctx.shape = (f, c, h, w)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _L()
+        (idx,) = ctx.saved_tensors
+        f, c, h, w = ctx.shape
+        g = g.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        dx = torch.empty((f, h, w, c), dtype=torch.bfloat16, device=g.device)
+        _lib.check(L.maxpool3x3s2_bwd(ptr(g), ptr(idx), ptr(dx), f, h, w, c, _stream()), "maxpool3x3s2_bwd")
+        return dx.permute(0, 3, 1, 2)
+
+
+def maxpool3x3s2(x):
+    return _MaxPool3x3s2.apply(x)
+
+
 def bn_enabled() -> bool:
     """MVFB_BN=0 routes BatchNorm / ReLU / residual back through torch (A/B measurements only)."""
     return os.environ.get("MVFB_BN", "1") != "0"

@@ -196,8 +196,20 @@ class ResNet(nn.Module):
         else:
             raise TypeError('pretrained must be a str or None')
 
+    def _stem(self, x):
+        """conv1 -> norm1 -> relu -> maxpool (resnet.py:481-484); own kernels in the bf16 configuration."""
+        from . import ops
+        if ops.stem_eligible(x, self.conv1):
+            out, sums = ops.stem_conv(x, self.conv1.weight, True)
+        else:
+            out, sums = self.conv1(x), None
+        out = _bn_act(self.norm1, out, True, sums=sums, relu_module=self.relu)
+        if ops.maxpool_eligible(out, self.maxpool):
+            return ops.maxpool3x3s2(out)
+        return self.maxpool(out)
+
     def forward(self, x):
-        x = self.maxpool(_bn_act(self.norm1, self.conv1(x), True, relu_module=self.relu))
+        x = self._stem(x)
         outs = []
         for i, name in enumerate(self.res_layers):
             x = getattr(self, name)(x)

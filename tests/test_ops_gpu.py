@@ -230,3 +230,51 @@ def test_strided_1x1_downsample(F, Cin, Cout, H):
     assert rel(sums[1], (y.detach().float() ** 2).sum((0, 2, 3))) < 1e-3
     assert rel(xo.grad, xr.grad) < 2e-2
     assert rel(wo.grad, wr.grad) < 2e-2
+
+
+# ------------------------------------------------------------------------------------------------ stem
+@pytest.mark.parametrize("F,H", [(2, 224), (3, 64), (1, 30)])
+def test_stem_conv_vs_torch(F, H):
+    """conv1 of the ResNet stem (im2col + tcgen05 GEMM, backbones/resnet.py:424) against torch's fp32 convolution of the
+    same bf16-rounded operands: output, the BatchNorm sums of the GEMM epilogue, and the weight gradient."""
+    from mvfnet_b200 import ops
+    g = torch.Generator().manual_seed(7 + F + H)
+    x = torch.randn((F, 3, H, H + 2), generator=g).cuda()
+    w = (torch.randn((64, 3, 7, 7), generator=g) * 0.1).cuda().requires_grad_(True)
+    conv = torch.nn.Conv2d(3, 64, 7, 2, 3, bias=False).cuda()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert ops.stem_eligible(x, conv)
+        y, sums = ops.stem_conv(x, w, True)
+    xr, wr = x.bfloat16().float(), w.detach().bfloat16().float().requires_grad_(True)
+    ref = torch.nn.functional.conv2d(xr, wr, stride=2, padding=3)
+    assert y.shape == ref.shape and y.dtype == torch.bfloat16 and y.is_contiguous(memory_format=torch.channels_last)
+    scale = ref.abs().max().item()
+    assert (y.float() - ref).abs().max().item() < 1e-2 * scale
+    yf = y.float()
+    assert torch.allclose(sums[0], yf.sum(dim=(0, 2, 3)), rtol=2e-3, atol=2e-3 * scale * yf[:, 0].numel() ** 0.5)
+    assert torch.allclose(sums[1], (yf * yf).sum(dim=(0, 2, 3)), rtol=2e-3)
+    gy = torch.randn(ref.shape, generator=g).cuda().bfloat16().contiguous(memory_format=torch.channels_last)
+    y.backward(gy)
+    ref.backward(gy.float())
+    assert (w.grad - wr.grad).abs().max().item() < 1e-2 * wr.grad.abs().max().item()
+
+
+@pytest.mark.parametrize("F,C,H,W", [(2, 64, 112, 112), (3, 16, 9, 14), (1, 8, 5, 5)])
+def test_maxpool3x3s2_vs_torch(F, C, H, W):
+    """MaxPool2d(3, 2, 1) forward and backward against ATen on inputs full of ties (post-ReLU zeros, repeated values):
+    the recorded arg-max must follow ATen's first-maximum rule, so both directions are bit-exact."""
+    from mvfnet_b200 import ops
+    g = torch.Generator().manual_seed(11 + C + H)
+    x = torch.randint(-3, 4, (F, C, H, W), generator=g).float().clamp_min(0) * 0.5
+    x = x.cuda().bfloat16().contiguous(memory_format=torch.channels_last)
+    pool = torch.nn.MaxPool2d(3, 2, 1)
+    assert ops.maxpool_eligible(x, pool)
+    xa = x.clone().requires_grad_(True)
+    xb = x.clone().requires_grad_(True)
+    ya = ops.maxpool3x3s2(xa)
+    yb = pool(xb)
+    assert ya.shape == yb.shape and torch.equal(ya, yb)
+    gy = torch.randn(yb.shape, generator=g).cuda().bfloat16().contiguous(memory_format=torch.channels_last)
+    ya.backward(gy)
+    yb.backward(gy)
+    assert torch.equal(xa.grad, xb.grad)
