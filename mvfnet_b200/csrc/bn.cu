@@ -143,12 +143,14 @@ bn_apply_kernel(const ApplyArgs a) {
   }
   const long long stride = (long long)gridDim.x * rows_par;
   const int co = vec * 8;
-  for (long long r = (long long)blockIdx.x * rows_par + rowlane; r < a.M; r += stride) {
+  // four rows per iteration, every load issued before the first use: ~100 KB in flight per SM (the kernel is
+  // register-limited to a few CTAs per SM, one row at a time left HBM latency exposed: 64-69 % of the copy rate)
+  auto body = [&](long long r, const uint4& xq, const uint4& rq) {
     float f[8];
-    unpack8(ldg16(a.x + r * a.ldx + co), f);
+    unpack8(xq, f);
     if (a.res) {
       float g[8];
-      unpack8(ldg16(a.res + r * a.ldr + co), g);
+      unpack8(rq, g);
 #pragma unroll
       for (int j = 0; j < 8; ++j) f[j] = fmaf(f[j], scale[j], shift[j]) + g[j];
     } else {
@@ -166,7 +168,19 @@ bn_apply_kernel(const ApplyArgs a) {
       }
     }
     *reinterpret_cast<uint4*>(a.y + r * a.ldy + co) = pack8(f);
+  };
+  long long r = (long long)blockIdx.x * rows_par + rowlane;
+  for (; r + 3 * stride < a.M; r += 4 * stride) {
+    uint4 xq[4], rq[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) xq[u] = ldg16(a.x + (r + u * stride) * a.ldx + co);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) rq[u] = a.res ? ldg16(a.res + (r + u * stride) * a.ldr + co) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) body(r + u * stride, xq[u], rq[u]);
   }
+  for (; r < a.M; r += stride)
+    body(r, ldg16(a.x + r * a.ldx + co), a.res ? ldg16(a.res + r * a.ldr + co) : make_uint4(0, 0, 0, 0));
 }
 
 // ---------------------------------------------------------------- backward
@@ -199,18 +213,16 @@ bn_bwd_reduce_kernel(const BwdArgs a) {
     }
     const long long stride = (long long)gridDim.x * rows_par;
     const int co = vec * 8;
-    for (long long r = (long long)blockIdx.x * rows_par + rowlane; r < a.M; r += stride) {
+    auto body = [&](const uint4& gq, const uint4& xq, uint32_t bits, const uint4& yq) {
       float gv[8], xv[8];
-      const uint4 gq = ldg16(a.g + r * a.ldg + co), xq = ldg16(a.x + r * a.ldx + co);
       unpack8(gq, gv);
       unpack8(xq, xv);
       if (a.mask) {
-        const uint32_t bits = __ldg(a.mask + r * vecs + vec);
 #pragma unroll
         for (int j = 0; j < 8; ++j) gv[j] = (bits >> j) & 1u ? gv[j] : 0.f;
       } else if (a.y) {
         float yv[8];
-        unpack8(ldg16(a.y + r * a.ldy + co), yv);
+        unpack8(yq, yv);
 #pragma unroll
         for (int j = 0; j < 8; ++j) gv[j] = yv[j] > 0.f ? gv[j] : 0.f;
       }
@@ -219,7 +231,26 @@ bn_bwd_reduce_kernel(const BwdArgs a) {
         acc[j] += gv[j];
         acc[8 + j] = fmaf(gv[j], fmaf(xv[j], rs[j], mr[j]), acc[8 + j]);
       }
+    };
+    const uint4 z4 = make_uint4(0, 0, 0, 0);
+    long long r = (long long)blockIdx.x * rows_par + rowlane;
+    for (; r + 3 * stride < a.M; r += 4 * stride) {             // four rows per iteration, loads first
+      uint4 gq[4], xq[4], yq[4];
+      uint32_t bits[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const long long ru = r + u * stride;
+        gq[u] = ldg16(a.g + ru * a.ldg + co);
+        xq[u] = ldg16(a.x + ru * a.ldx + co);
+        bits[u] = a.mask ? __ldg(a.mask + ru * vecs + vec) : 0u;
+        yq[u] = (!a.mask && a.y) ? ldg16(a.y + ru * a.ldy + co) : z4;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) body(gq[u], xq[u], bits[u], yq[u]);
     }
+    for (; r < a.M; r += stride)
+      body(ldg16(a.g + r * a.ldg + co), ldg16(a.x + r * a.ldx + co), a.mask ? __ldg(a.mask + r * vecs + vec) : 0u,
+           (!a.mask && a.y) ? ldg16(a.y + r * a.ldy + co) : z4);
   }
   column_reduce_atomic<16>(acc, vecs, rows_par, vec, rowlane, a.sums, a.C, scratch);
 }
@@ -249,18 +280,16 @@ bn_bwd_apply_kernel(const BwdArgs a) {
   }
   const long long stride = (long long)gridDim.x * rows_par;
   const int co = vec * 8;
-  for (long long r = (long long)blockIdx.x * rows_par + rowlane; r < a.M; r += stride) {
+  auto body = [&](long long r, const uint4& gq, const uint4& xq, uint32_t bits, const uint4& yq) {
     float gv[8], xv[8];
-    const uint4 gq = ldg16(a.g + r * a.ldg + co), xq = ldg16(a.x + r * a.ldx + co);
     unpack8(gq, gv);
     unpack8(xq, xv);
     if (a.mask) {
-      const uint32_t bits = __ldg(a.mask + r * vecs + vec);
 #pragma unroll
       for (int j = 0; j < 8; ++j) gv[j] = (bits >> j) & 1u ? gv[j] : 0.f;
     } else if (a.y) {
       float yv[8];
-      unpack8(ldg16(a.y + r * a.ldy + co), yv);
+      unpack8(yq, yv);
 #pragma unroll
       for (int j = 0; j < 8; ++j) gv[j] = yv[j] > 0.f ? gv[j] : 0.f;
     }
@@ -272,7 +301,26 @@ bn_bwd_apply_kernel(const BwdArgs a) {
       o[j] = ga[j] * (gv[j] - b[j] - xh * cc[j]);
     }
     *reinterpret_cast<uint4*>(a.dx + r * a.lddx + co) = pack8(o);
+  };
+  const uint4 z4 = make_uint4(0, 0, 0, 0);
+  long long r = (long long)blockIdx.x * rows_par + rowlane;
+  for (; r + 3 * stride < a.M; r += 4 * stride) {               // four rows per iteration, loads first
+    uint4 gq[4], xq[4], yq[4];
+    uint32_t bits[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long ru = r + u * stride;
+      gq[u] = ldg16(a.g + ru * a.ldg + co);
+      xq[u] = ldg16(a.x + ru * a.ldx + co);
+      bits[u] = a.mask ? __ldg(a.mask + ru * vecs + vec) : 0u;
+      yq[u] = (!a.mask && a.y) ? ldg16(a.y + ru * a.ldy + co) : z4;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) body(r + u * stride, gq[u], xq[u], bits[u], yq[u]);
   }
+  for (; r < a.M; r += stride)
+    body(r, ldg16(a.g + r * a.ldg + co), ldg16(a.x + r * a.ldx + co), a.mask ? __ldg(a.mask + r * vecs + vec) : 0u,
+         (!a.mask && a.y) ? ldg16(a.y + r * a.ldy + co) : z4);
 }
 
 // rows x cols strided 2-D copy in 16-byte vectors (cols % 8 == 0): y[r, :cols] = x[r, :cols]
