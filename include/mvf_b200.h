@@ -123,6 +123,12 @@ typedef struct {
 int conv1x1_gemm(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, void* out, float* colsum,
                  float* colsq, mvfb_stream_t stream);
 
+/* out = A B^T + res: the same GEMM with an (M, N) bf16 addend (leading dimension ldr) read in the epilogue.  Used as
+ * the input-gradient of conv1 of a Bottleneck whose input also feeds the identity path: dL/dx = dY W + dL/d(identity)
+ * in one pass instead of a GEMM and a separate full-tensor add (backbones/resnet.py:211-213, 238). */
+int conv1x1_gemm_add(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, const void* res,
+                     long long ldr, void* out, mvfb_stream_t stream);
+
 /* Weight gradient of the same layer: dw[n, k] = sum_m g[m*ldb + n] * X[m, k], X = [x0[:, :K0] | x1[:, K0:]] as above
  * (M = pixels, N = Cout, K = Cin; lda0 / lda1 / ldb = leading dimensions of x0 / x1 / g; dw is fp32 (N, ldd) and is
  * zeroed by the call, then accumulated with fp32 atomics over split-K partitions of the pixel axis).  Both MMA

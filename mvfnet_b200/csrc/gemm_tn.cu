@@ -39,6 +39,8 @@ struct GemmArgs {
   int m_tiles, n_tiles;
   float* colsum;                   // [N] or null
   float* colsq;                    // [N] or null
+  const __nv_bfloat16* res;        // optional (M, N) bf16 addend, leading dimension ldr: out = A B^T + res
+  long long ldr;
   // 3x3 convolution as an implicit GEMM (IM2COL kernels): K = 9 * Cin ordered (r, s, c); A tiles are gathered by
   // TMA im2col loads from the NHWC input, M = F * Ho * Wo output pixels
   int Cin, Ho, Wo, stride, ks, pad;   // ks = 3 (pad 1) or 1 (pad 0)
@@ -178,6 +180,15 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
+      // optional addend (out = A B^T + res): this thread's row of it, 32 columns (64 contiguous bytes) per chunk; the
+      // first chunk is requested before the accumulator is waited for
+      const long long grow = (long long)mt * BM + row;
+      const uint4* res_row = (a.res && grow < a.M) ? reinterpret_cast<const uint4*>(a.res + grow * a.ldr + nt * BN) : nullptr;
+      uint4 rq[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+      if (res_row) {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rq[q] = __ldg(res_row + q);
+      }
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
       // staging tile of the previous store must have been read by the TMA engine
@@ -187,8 +198,27 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t v[32];
+        // the addend of the NEXT 32 columns is requested now, a whole chunk ahead of its use
+        uint4 rn[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
+        if (res_row && c0 + 32 < BN) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rn[q] = __ldg(res_row + (c0 + 32) / 8 + q);
+        }
         tmem_ld_32x32b_x32(taddr + c0, v);
         tmem_ld_wait();
+        if (res_row) {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint32_t w4[4] = {rq[q].x, rq[q].y, rq[q].z, rq[q].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              v[q * 8 + 2 * e] = __float_as_uint(__uint_as_float(v[q * 8 + 2 * e]) + bf16_lo(w4[e]));
+              v[q * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(v[q * 8 + 2 * e + 1]) + bf16_hi(w4[e]));
+            }
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q) rq[q] = rn[q];
+        }
         // 32 fp32 -> 32 bf16 = 64 B = four 16-byte chunks of this row in panel c0/64
         uint8_t* panel = staging + (size_t)(c0 >> 6) * (BM * 128) + (size_t)row * 128;
         const int chunk0 = (c0 & 63) >> 3;
@@ -271,8 +301,8 @@ int launch_kernel(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtens
 }
 
 template <int BN>
-int launch(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, void* out, float* colsum,
-           float* colsq, cudaStream_t st) {
+int launch(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, const void* res, long long ldr,
+           void* out, float* colsum, float* colsq, cudaStream_t st) {
   using C = Cfg<BN>;
   CUtensorMap tmA0, tmA1, tmB, tmD;
   int rc;
@@ -288,6 +318,7 @@ int launch(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* 
   GemmArgs a;
   a.M = d->M; a.N = d->N; a.K = d->K; a.K0 = d->K0;
   a.colsum = colsum; a.colsq = colsq;
+  a.res = (const __nv_bfloat16*)res; a.ldr = ldr;
   a.Cin = a.Ho = a.Wo = a.stride = a.pad = 0;
   a.ks = 1;
   return launch_kernel<BN, false>(tmA0, tmA1, tmB, tmD, a, st);
@@ -313,6 +344,7 @@ int launch_conv3x3(const mvfb_conv_desc* d, const void* x, const void* w, void* 
   GemmArgs a;
   a.M = M; a.N = d->Cout; a.K = taps * d->Cin; a.K0 = 0;
   a.colsum = colsum; a.colsq = colsq;
+  a.res = nullptr; a.ldr = 0;
   a.Cin = d->Cin; a.Ho = Ho; a.Wo = Wo; a.stride = d->stride; a.ks = d->ksize; a.pad = pad;
   return launch_kernel<BN, true>(tmA, tmA, tmB, tmD, a, st);
 }
@@ -323,8 +355,8 @@ int launch_conv3x3(const mvfb_conv_desc* d, const void* x, const void* w, void* 
 
 using namespace mvfb;
 
-extern "C" int conv1x1_gemm(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, void* out,
-                            float* colsum, float* colsq, mvfb_stream_t stream) {
+static int conv1x1_gemm_impl(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, const void* res,
+                             long long ldr, void* out, float* colsum, float* colsq, mvfb_stream_t stream) {
   MVFB_CHECK(d && a1 && b && out, MVFB_ERR_ARG, "null descriptor / operand");
   MVFB_CHECK(d->M > 0 && d->N > 0 && d->K > 0, MVFB_ERR_ARG, "bad GEMM shape M=%lld N=%d K=%d", d->M, d->N, d->K);
   MVFB_CHECK(d->K % BK == 0 && d->K0 % BK == 0 && d->K0 >= 0 && d->K0 < d->K, MVFB_ERR_UNSUPPORTED,
@@ -336,10 +368,23 @@ extern "C" int conv1x1_gemm(const mvfb_gemm_desc* d, const void* a0, const void*
              "leading dimensions must be multiples of 8 elements (16 bytes)");
   MVFB_CHECK(!((uintptr_t)a1 & 15) && !((uintptr_t)b & 15) && !((uintptr_t)out & 15) && !((uintptr_t)a0 & 15),
              MVFB_ERR_UNSUPPORTED, "operands must be 16-byte aligned");
+  MVFB_CHECK(!res || (!((uintptr_t)res & 15) && ldr % 8 == 0 && ldr >= d->N), MVFB_ERR_UNSUPPORTED,
+             "the addend must be 16-byte aligned with a leading dimension that is a multiple of 8 and >= N");
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->N % 256 == 0) return launch<256>(d, a0, a1, b, out, colsum, colsq, st);
-  if (d->N % 128 == 0) return launch<128>(d, a0, a1, b, out, colsum, colsq, st);
-  return launch<64>(d, a0, a1, b, out, colsum, colsq, st);
+  if (d->N % 256 == 0) return launch<256>(d, a0, a1, b, res, ldr, out, colsum, colsq, st);
+  if (d->N % 128 == 0) return launch<128>(d, a0, a1, b, res, ldr, out, colsum, colsq, st);
+  return launch<64>(d, a0, a1, b, res, ldr, out, colsum, colsq, st);
+}
+
+extern "C" int conv1x1_gemm(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, void* out,
+                            float* colsum, float* colsq, mvfb_stream_t stream) {
+  return conv1x1_gemm_impl(d, a0, a1, b, nullptr, 0, out, colsum, colsq, stream);
+}
+
+extern "C" int conv1x1_gemm_add(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, const void* res,
+                                long long ldr, void* out, mvfb_stream_t stream) {
+  MVFB_CHECK(res != nullptr, MVFB_ERR_ARG, "conv1x1_gemm_add needs the addend");
+  return conv1x1_gemm_impl(d, a0, a1, b, res, ldr, out, nullptr, nullptr, stream);
 }
 
 extern "C" int conv3x3_gemm(const mvfb_conv_desc* d, const void* x, const void* w, void* out, float* colsum,

@@ -59,6 +59,8 @@ def _L():
         L.bn_bwd.restype = C.c_int
         L.bn_bwd.argtypes = [C.POINTER(BnDesc), _VP, _LL, _VP, _LL, _VP, _LL, _VP, _VP, _VP, _VP, _LL, _VP, _LL, _VP,
                              _VP, _VP, _VP, _VP]
+        L.conv1x1_gemm_add.restype = C.c_int
+        L.conv1x1_gemm_add.argtypes = [C.POINTER(GemmDesc), _VP, _VP, _VP, _VP, _LL, _VP, _VP]
         L.stem_im2col.restype = C.c_int
         L.stem_im2col.argtypes = [_VP, _VP, _LL, C.c_int, C.c_int, _VP]
         L.maxpool3x3s2_fwd.restype = C.c_int
@@ -89,9 +91,9 @@ def eligible(x, cin, cout):
             and x.is_contiguous(memory_format=torch.channels_last) and x.shape[1] == cin)
 
 
-def gemm_tn(a1, b, a0=None, k0=0, stats=False, out=None):
-    """out[m, n] = sum_k A[m, k] b[n, k] with A = [a0[:, :k0] | a1[:, k0:]]; 2-D bf16 tensors whose last dim is
-    contiguous.  Returns (out, colsum, colsq) -- the sums are None unless `stats`."""
+def gemm_tn(a1, b, a0=None, k0=0, stats=False, out=None, add=None):
+    """out[m, n] = sum_k A[m, k] b[n, k] (+ add[m, n]) with A = [a0[:, :k0] | a1[:, k0:]]; 2-D bf16 tensors whose last
+    dim is contiguous.  Returns (out, colsum, colsq) -- the sums are None unless `stats`."""
     L = _L()
     m, k = a1.shape
     n = b.shape[0]
@@ -106,10 +108,22 @@ def gemm_tn(a1, b, a0=None, k0=0, stats=False, out=None):
     if stats:
         sums = torch.zeros((2, n), dtype=torch.float32, device=a1.device)
         colsum, colsq = sums[0], sums[1]
+    if add is not None:
+        assert not stats and add.shape == (m, n) and add.stride(1) == 1 and add.dtype == torch.bfloat16
+        rc = L.conv1x1_gemm_add(C.byref(d), ptr(a0), ptr(a1), ptr(b), ptr(add), add.stride(0), ptr(out), _stream())
+        _lib.check(rc, "conv1x1_gemm_add")
+        return out, None, None
     rc = L.conv1x1_gemm(C.byref(d), ptr(a0), ptr(a1), ptr(b), ptr(out), ptr(colsum), ptr(colsq),
                         C.c_void_p(torch.cuda.current_stream().cuda_stream))
     _lib.check(rc, "conv1x1_gemm")
     return out, colsum, colsq
+
+
+def add_fusion_enabled() -> bool:
+    """MVFB_ADDFUSE=1 folds the sum of the two gradients of a Bottleneck's input into the input-gradient GEMM's epilogue
+    (conv1x1_gemm_add).  Off by default: measured neutral on B200 (91.0 vs 91.4 ms per step) -- the K = 64 dgrad GEMMs
+    of layer1 are epilogue-bound and pay for the addend's row-wise reads what autograd's coalesced add kernel cost."""
+    return os.environ.get("MVFB_ADDFUSE", "0") == "1"
 
 
 def wgrad_enabled() -> bool:
@@ -142,38 +156,50 @@ def _nhwc_from_rows(rows, f, h, w):
 
 
 class _Conv1x1(torch.autograd.Function):
+    """1x1 stride-1 convolution on the tcgen05 GEMM.  `passthrough`: also returns an alias of x -- the Bottleneck
+    uses THAT as its identity path, so both gradients of the block input arrive in this node and the input-gradient
+    GEMM adds dL/d(identity) in its epilogue (conv1x1_gemm_add) instead of autograd running a full-tensor add."""
+
     @staticmethod
-    def forward(ctx, x, weight, stats):
+    def forward(ctx, x, weight, stats, passthrough):
         f, cin, h, w = x.shape
         wb = weight.detach().reshape(weight.shape[0], cin).to(torch.bfloat16)
         out, colsum, _ = gemm_tn(_rows(x), wb, stats=stats)
         ctx.save_for_backward(x, wb)
-        y = _nhwc_from_rows(out, f, h, w)
-        if not stats:
-            return y
-        sums = colsum._base if colsum._base is not None else colsum     # the (2, N) buffer
-        ctx.mark_non_differentiable(sums)
-        return y, sums
+        ctx.stats, ctx.passthrough = stats, passthrough
+        outs = [_nhwc_from_rows(out, f, h, w)]
+        if stats:
+            sums = colsum._base if colsum._base is not None else colsum     # the (2, N) buffer
+            ctx.mark_non_differentiable(sums)
+            outs.append(sums)
+        if passthrough:
+            outs.append(x.view_as(x))
+        return outs[0] if len(outs) == 1 else tuple(outs)
 
     @staticmethod
-    def backward(ctx, g, *unused):
+    def backward(ctx, g, *rest):
         x, wb = ctx.saved_tensors
         f, cin, h, w = x.shape
+        g_id = rest[-1] if ctx.passthrough else None
         g = g.contiguous(memory_format=torch.channels_last)
         g2 = _rows(g)
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dx2, _, _ = gemm_tn(g2, wb.t().contiguous())               # dX = dY W  ==  TN GEMM against W^T
+            add = None
+            if g_id is not None:
+                add = _rows(g_id.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
+            dx2, _, _ = gemm_tn(g2, wb.t().contiguous(), add=add)      # dX = dY W (+ dL/d identity)  ==  TN GEMM against W^T
             dx = _nhwc_from_rows(dx2, f, h, w)
         if ctx.needs_input_grad[1]:
             dw = gemm_wgrad(g2, _rows(x)).view(wb.shape[0], cin, 1, 1)
-        return dx, dw, None
+        return dx, dw, None, None
 
 
-def conv1x1(x, weight, stats=False):
+def conv1x1(x, weight, stats=False, passthrough=False):
     """1x1 stride-1 bias-free convolution of a bf16 channels_last tensor on the tcgen05 GEMM.  With `stats` also
-    returns the (2, Cout) per-channel (sum, sum of squares) of the output, accumulated in the GEMM epilogue."""
-    return _Conv1x1.apply(x, weight, stats)
+    returns the (2, Cout) per-channel (sum, sum of squares) of the output, accumulated in the GEMM epilogue; with
+    `passthrough` the last element of the result is an alias of x to be used as the residual identity."""
+    return _Conv1x1.apply(x, weight, stats, passthrough)
 
 
 class _MVFConv1x1(torch.autograd.Function):

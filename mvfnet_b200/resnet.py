@@ -28,6 +28,17 @@ def constant_init(module, val, bias=0):
         nn.init.constant_(module.bias, bias)
 
 
+def _conv1x1_id(conv, x):
+    """conv1 of a Bottleneck in the fused configuration: (out, sums, identity) where `identity` aliases x and carries
+    its gradient back into the convolution's own backward (ops._Conv1x1); None when the layer is not eligible."""
+    from . import ops
+    if (type(conv) is nn.Conv2d and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.bias is None
+            and conv.groups == 1 and ops.eligible(x, conv.in_channels, conv.out_channels) and x.requires_grad
+            and torch.is_grad_enabled() and ops.add_fusion_enabled()):
+        return ops.conv1x1(x, conv.weight, True, True)
+    return None
+
+
 def _conv1x1(conv, x, want_stats=False):
     """Run a 1x1 stride-1 nn.Conv2d (or the MVF wrapper around one) on the tcgen05 GEMM when the activation is
     bf16 channels_last (the training / inference configuration); anything else (strided down-sampling, fp32
@@ -109,7 +120,12 @@ class Bottleneck(nn.Module):
         """resnet.py:208-244.  `self.conv1` is the MVF wrapper in the stages `mvf_freq` selects."""
         fuse = x.is_cuda and x.dtype == torch.bfloat16
         identity = x
-        out, sums = _conv1x1(self.conv1, x, fuse)
+        fused = _conv1x1_id(self.conv1, x) if fuse else None
+        if fused is not None:
+            out, sums, identity = fused          # the identity / down-sample path reads the alias: one fused gradient
+            x = identity
+        else:
+            out, sums = _conv1x1(self.conv1, x, fuse)
         out = _bn_act(self.norm1, out, True, sums=sums, relu_module=self.relu)
         out, sums = _conv3x3(self.conv2, out, fuse)
         out = _bn_act(self.norm2, out, True, sums=sums, relu_module=self.relu)

@@ -278,3 +278,18 @@ def test_maxpool3x3s2_vs_torch(F, C, H, W):
     ya.backward(gy)
     yb.backward(gy)
     assert torch.equal(xa.grad, xb.grad)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 64, 64), (12544, 256, 64), (1000, 128, 256)])
+def test_gemm_add_epilogue(M, N, K):
+    """conv1x1_gemm_add: out = A B^T + addend (the fused gradient sum at a Bottleneck's input), M tail included."""
+    from mvfnet_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn((M, K), generator=g).cuda().bfloat16()
+    b = (torch.randn((N, K), generator=g) * 0.1).cuda().bfloat16()
+    r = torch.randn((M, N), generator=g).cuda().bfloat16()
+    out, _, _ = ops.gemm_tn(a, b, add=r)
+    ref = a.float() @ b.float().t() + r.float()
+    assert (out.float() - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
+    plain, _, _ = ops.gemm_tn(a, b)
+    assert not torch.equal(out, plain)
