@@ -25,17 +25,20 @@ namespace {
 constexpr int kStemK = 147, kStemKp = 192;
 
 // x: (F, H, W, 3) bf16 NHWC.  One thread per (output pixel, 8-element chunk of the 192-wide row).
+// I = index type of the flattened work item: unsigned 32-bit whenever the launch has fewer than 2^31 items (64-bit
+// division / modulo costs ~100 instructions each and made these kernels instruction-bound: im2col 3.7 ms)
+template <typename I>
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ a, int H, int W, int Ho, int Wo,
                    long long total) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int chunk = (int)(i % (kStemKp / 8));
-  const long long row = i / (kStemKp / 8);
-  const int ow = (int)(row % Wo);
-  const long long t = row / Wo;
-  const int oh = (int)(t % Ho);
-  const long long f = t / Ho;
+  const I i = (I)blockIdx.x * (I)blockDim.x + threadIdx.x;
+  if ((long long)i >= total) return;
+  const int chunk = (int)(i % (I)(kStemKp / 8));
+  const I row = i / (I)(kStemKp / 8);
+  const int ow = (int)(row % (I)Wo);
+  const I t = row / (I)Wo;
+  const int oh = (int)(t % (I)Ho);
+  const long long f = (long long)(t / (I)Ho);
   const int rowlen = W * 3;
   const int e0 = (2 * ow - 3) * 3;                              // element offset of kw = 0, c = 0 inside an image row
   const unsigned short* img = reinterpret_cast<const unsigned short*>(x) + f * (long long)H * rowlen;
@@ -59,16 +62,17 @@ __device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v <<
 __device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
 // x: (F, H, W, C) bf16 NHWC -> y: (F, Ho, Wo, C), idx: (F, Ho, Wo, C) bytes.  One thread per (output pixel, 8 channels).
+template <typename I>
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint2* __restrict__ idx, int H, int W, int Ho,
                    int Wo, int C8, long long total) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c8 = (int)(i % C8);
-  long long t = i / C8;
-  const int ow = (int)(t % Wo); t /= Wo;
-  const int oh = (int)(t % Ho);
-  const long long f = t / Ho;
+  const I i = (I)blockIdx.x * (I)blockDim.x + threadIdx.x;
+  if ((long long)i >= total) return;
+  const int c8 = (int)(i % (I)C8);
+  I t = i / (I)C8;
+  const int ow = (int)(t % (I)Wo); t /= (I)Wo;
+  const int oh = (int)(t % (I)Ho);
+  const long long f = (long long)(t / (I)Ho);
   float best[8];
   int arg[8];
 #pragma unroll
@@ -105,16 +109,17 @@ maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint2* __
 }
 
 // dx[f, ih, iw, c] = sum over the windows (oh, ow) that contain (ih, iw) of g[f, oh, ow, c] * [idx[f, oh, ow, c] == position]
+template <typename I>
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const uint4* __restrict__ g, const uint2* __restrict__ idx, uint4* __restrict__ dx, int H, int W,
                    int Ho, int Wo, int C8, long long total) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int c8 = (int)(i % C8);
-  long long t = i / C8;
-  const int iw = (int)(t % W); t /= W;
-  const int ih = (int)(t % H);
-  const long long f = t / H;
+  const I i = (I)blockIdx.x * (I)blockDim.x + threadIdx.x;
+  if ((long long)i >= total) return;
+  const int c8 = (int)(i % (I)C8);
+  I t = i / (I)C8;
+  const int iw = (int)(t % (I)W); t /= (I)W;
+  const int ih = (int)(t % (I)H);
+  const long long f = (long long)(t / (I)H);
   float acc[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) acc[e] = 0.f;
@@ -166,8 +171,12 @@ int stem_im2col(const void* x, void* a, long long F, int H, int W, mvfb_stream_t
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
   const long long total = F * Ho * Wo * (kStemKp / 8);
   const unsigned blocks = (unsigned)ceil_div_ll(total, 256);
-  stem_im2col_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)a, H, W, Ho, Wo,
-                                                                total);
+  if (total < (1LL << 31))
+    stem_im2col_kernel<uint32_t><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)a, H, W, Ho,
+                                                                           Wo, total);
+  else
+    stem_im2col_kernel<long long><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)a, H, W, Ho,
+                                                                            Wo, total);
   count_launch();
   MVFB_LAUNCH_CHECK();
   return MVFB_OK;
@@ -179,8 +188,12 @@ int maxpool3x3s2_fwd(const void* x, void* y, void* idx, long long F, int H, int 
              MVFB_ERR_ARG, "maxpool3x3s2_fwd: misaligned tensors");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = F * Ho * Wo * (C / 8);
-  maxpool_fwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const uint4*)x, (uint4*)y, (uint2*)idx, H, W, Ho, Wo, C / 8, total);
+  if (total < (1LL << 31))
+    maxpool_fwd_kernel<uint32_t><<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)x, (uint4*)y, (uint2*)idx, H, W, Ho, Wo, C / 8, total);
+  else
+    maxpool_fwd_kernel<long long><<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)x, (uint4*)y, (uint2*)idx, H, W, Ho, Wo, C / 8, total);
   count_launch();
   MVFB_LAUNCH_CHECK();
   return MVFB_OK;
@@ -192,8 +205,12 @@ int maxpool3x3s2_bwd(const void* g, const void* idx, void* dx, long long F, int 
              MVFB_ERR_ARG, "maxpool3x3s2_bwd: misaligned tensors");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
   const long long total = F * H * W * (C / 8);
-  maxpool_bwd_kernel<<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      (const uint4*)g, (const uint2*)idx, (uint4*)dx, H, W, Ho, Wo, C / 8, total);
+  if (total < (1LL << 31))
+    maxpool_bwd_kernel<uint32_t><<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)g, (const uint2*)idx, (uint4*)dx, H, W, Ho, Wo, C / 8, total);
+  else
+    maxpool_bwd_kernel<long long><<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)g, (const uint2*)idx, (uint4*)dx, H, W, Ho, Wo, C / 8, total);
   count_launch();
   MVFB_LAUNCH_CHECK();
   return MVFB_OK;
