@@ -511,13 +511,14 @@ mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
         if (part < parts) {
           double accd = 0.0;
           const long long t0 = clock64();
-          for (int r0 = part; r0 < rows; r0 += 4 * parts) {
-            uint2 v[4];
+          constexpr int kBatch = 16;                            // rows polled per round trip (wide groups have parts = 1)
+          for (int r0 = part; r0 < rows; r0 += kBatch * parts) {
+            uint2 v[kBatch];
             bool ok;
             do {
               ok = true;
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
+              for (int u = 0; u < kBatch; ++u) {
                 const int r = r0 + u * parts;
                 v[u] = make_uint2(0u, a.epoch);
                 if (r < rows) v[u] = ld_relaxed_v2(a.partials + ((size_t)r * g.ngroups + cg) * per + k);
@@ -525,8 +526,8 @@ mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
               }
               if (!ok && clock64() - t0 > 4000000000LL) __trap();  // a CTA that never arrives must not hang the GPU
             } while (!ok);
-            accd += ((double)__uint_as_float(v[0].x) + (double)__uint_as_float(v[1].x)) +
-                    ((double)__uint_as_float(v[2].x) + (double)__uint_as_float(v[3].x));
+#pragma unroll
+            for (int u = 0; u < kBatch; ++u) accd += (double)__uint_as_float(v[u].x);
           }
           s_dpart[part * per + k] = accd;
         }
