@@ -304,11 +304,13 @@ def run_ours(args):
 
     a_f, us_f, n_f = agg(fwd)
     a_b, us_b, n_b = agg(bwd)
-    roofline = {"bound": "hbm", "kernel": "mvf_fwd (fused T/H/W stencil + BN3d + hardswish)", "achieved": a_f,
+    roofline = {"bound": "hbm", "kernel": "mvf_fwd = mvf_sweep_kernel (fused T/H/W stencil + train-mode BN3d + hardswish, one cooperative launch)", "achieved": a_f,
                 "peak": peak, "unit": "GB/s", "frac": (a_f / peak) if a_f else None,
-                # ncu --set full (profiles/r01_mvf_v3_stream_ncu_full.csv): dram read+write of the stats+apply pair is
-                # 1.015x the algorithmic bytes (second pass served by L2); scaled to this run's mean launch
-                "traffic": (1.015 * sum(r[0] for r in fwd) / len(fwd)) if fwd else None,
+                # ncu --set full (profiles/r01_mvf_v4_sweep_ncu_full.csv, train-mode launch, 14x14 slab, 128 clips):
+                # dram read 53.1 MB + write 6.0 MB per launch against 102.8 MB algorithmic -- x is read once (the second
+                # sweep is served by L2) and most of the result slab is still dirty in L2 when the kernel ends, the
+                # consumer GEMM reads it from there.  Scaled to this run's mean launch.
+                "traffic": (0.575 * sum(r[0] for r in fwd) / len(fwd)) if fwd else None,
                 "peak_source": peak_src, "launches_timed": n_f, "avg_launch_us": us_f,
                 "algorithmic_bytes": "2*E*s per launch (E = B*T*Cs*H*W slab elements, s = 2 B bf16), summed over "
                                      "the 9 MVF modules of R50",
