@@ -324,7 +324,8 @@ def run_ours(args):
                                    "clip+SGD step, B=%d clips per GPU%s" % (DEPTH, T_FRAMES, 64 // T_FRAMES, T_FRAMES, B,
                                    " (BASELINE.json configs[1])" if (DEPTH, T_FRAMES) == (50, 8) else ""),
                        "clips_per_gpu": B, "frames_per_gpu": B * T_FRAMES, "parallelism": "dp%d" % world,
-                       "l2": "no flush: one step streams >10 GB of activations, far above the 126 MB L2"},
+                       "l2": "no flush: one step streams >10 GB of activations, far above the 126 MB L2",
+                       "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 1)},
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
@@ -344,8 +345,8 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=128,
-                    help="clips per GPU (measured on B200: 64 -> 1098, 72 -> 1119, 96 -> 1150, 128 -> 1169 clips/s)")
+    ap.add_argument("--batch", type=int, default=160,
+                    help="clips per GPU (measured on B200, final build: 128 -> 1425, 160 -> 1471, 192 -> 1475 clips/s)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--depth", type=int, default=DEPTH, help="ResNet depth (50: BASELINE configs[1]; 101: configs[3])")
