@@ -22,8 +22,9 @@ def test_library_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "mvf_b200.h")).read()
     hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
     names = set(re.findall(r"\b([a-z_0-9]+)\s*\(", hdr)) - {"defined"}
-    names = {n for n in names if n.startswith(("mvf_", "mvfb_", "conv", "bn_", "sgd_", "gemm_"))}
-    assert {"mvf_fwd", "mvf_bwd", "mvf_b200_version", "mvf_b200_last_error"} <= names
+    names = {n for n in names if n.startswith(("mvf_", "mvfb_", "conv", "bn_", "sgd_", "gemm_", "stem_", "maxpool", "copy_"))}
+    assert {"mvf_fwd", "mvf_bwd", "mvf_b200_version", "mvf_b200_last_error", "conv1x1_gemm", "conv1x1_gemm_add",
+            "stem_im2col", "maxpool3x3s2_fwd", "maxpool3x3s2_bwd"} <= names
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for n in sorted(names):
         assert hasattr(lib, n), "libmvf_b200.so does not export %s" % n
@@ -43,6 +44,26 @@ def test_abi_argument_errors_without_gpu():
     assert rc == 1 and b"dtype" in L.mvf_b200_last_error()
     with pytest.raises(_lib.MvfB200Error):
         _lib.check(rc, "mvf_fwd")
+
+
+def test_stem_and_workspace_host_logic_without_gpu():
+    """Host-side logic of the entry points added with the generation-4 forward and the stem: argument validation
+    (no CUDA call is made for a rejected call) and the workspace the train-mode forward asks for -- one row of
+    2*Cg {value, epoch} words (8 bytes each) per CTA of a grid of at most one CTA per SM, for every R50 slab shape."""
+    from mvfnet_b200 import _lib, ops
+    L = ops._L()
+    assert L.stem_im2col(None, None, 4, 224, 224, None) == 1 and b"stem_im2col" in L.mvf_b200_last_error()
+    assert L.maxpool3x3s2_fwd(None, None, None, 4, 112, 112, 64, None) == 1
+    assert L.maxpool3x3s2_bwd(None, None, None, 4, 112, 112, 60, None) == 1      # C % 8 != 0 is rejected too
+    g = ops.GemmDesc()
+    g.M, g.N, g.K, g.K0, g.lda0, g.lda1, g.ldb, g.ldd = 128, 64, 64, 0, 0, 64, 64, 64
+    assert L.conv1x1_gemm_add(ctypes.byref(g), None, None, None, None, 64, None, None) == 1
+    for (C, H, Cs) in [(512, 28, 64), (1024, 14, 128), (2048, 7, 256)]:
+        d = _lib.MvfDesc(N=64, T=8, C=C, Cs=Cs, H=H, W=H, dtype=_lib.MVFB_BF16, layout=_lib.MVFB_NHWC, mode=2, use_hs=1,
+                         training=1, eps=1e-5, momentum=0.1)
+        nbytes = L.mvf_fwd_workspace_bytes(ctypes.byref(d))
+        assert nbytes >= 2 * Cs * 8                                   # at least one CTA row per channel group
+        assert nbytes <= 148 * 2 * 64 * 8 + 16 * 8 * Cs + 4096       # never more than one 64-channel row per SM (+ generic)
 
 
 def test_registry_contract():
