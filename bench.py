@@ -30,6 +30,10 @@ if ROOT not in sys.path:
 
 METRIC = "clips/sec (fwd+bwd) MVFNet-R50 8x8 224px"
 T_FRAMES, PX, DEPTH = 8, 224, 50
+# dram__bytes_read.sum + dram__bytes_write.sum of the train-mode mvf_sweep_kernel launch over its algorithmic bytes, from
+# the `ncu --set full` capture of THIS build named below (per launch, like `achieved`); None = not captured
+MVF_FWD_TRAFFIC_RATIO = None
+MVF_FWD_TRAFFIC_SOURCE = None
 
 
 def model_cfg(depth=DEPTH, t=T_FRAMES, dropout=0.5):
@@ -158,6 +162,114 @@ def run_reference(args):
     print(json.dumps(line))
 
 
+# --------------------------------------------------------------------------------------- GPU bar
+def gpu_bar(dev, world, rank, batches, steps=6, warmup=4):
+    """The north-star bar: the UNMODIFIED reference model (baseline/_ref, codes/models/modules/MVF.py:104-138 inside
+    codes/models/backbones/resnet.py:208-244, built from the config's model dict) on stock PyTorch / cuDNN on THIS
+    GPU: `.cuda()`, cudnn.benchmark (r50_dense.py:180), torch.autocast(bfloat16), weights in channels_last (the faster
+    of channels_last / contiguous is kept), and the same step as our arm: forward + backward (+ the reference's own
+    `allreduce_grads` when world > 1, core/dist_utils.py:38-49) + clip(40) + SGD-nesterov.  None of this library's
+    kernels is on that path.  Returns {"B<clips>": clips/s, ...} with the variant used."""
+    import contextlib
+    import io
+    import torch
+    import torch.distributed as dist
+    ref_root = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_root, "MVFNet", "codes")):
+        return {"unavailable": "baseline/_ref is missing (python tools/install_reference.py in the build container)"}
+    sys.path[:0] = [os.path.join(ref_root, "mmcv_stub"), os.path.join(ref_root, "MVFNet")]
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            from codes.models import build_recognizer as ref_build
+            from codes.core.dist_utils import allreduce_grads as ref_allreduce
+    except Exception as e:                                       # pragma: no cover
+        return {"unavailable": "reference import failed: %r" % (e,)}
+    torch.backends.cudnn.benchmark = True
+
+    def build(channels_last):
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = ref_build(model_cfg(DEPTH, T_FRAMES), None, None).to(dev).train()
+        if channels_last:
+            for p_ in m.parameters():
+                if p_.dim() == 4:
+                    p_.data = p_.data.contiguous(memory_format=torch.channels_last)
+        return m
+
+    def measure(m, B):
+        opt = torch.optim.SGD(m.parameters(), lr=0.015, momentum=0.9, weight_decay=1e-4, nesterov=True)
+        params = [p_ for p_ in m.parameters() if p_.requires_grad]
+        g = torch.Generator().manual_seed(2000 + rank)
+        img = torch.randn((B, T_FRAMES, 3, PX, PX), generator=g).to(dev)
+        label = torch.randint(0, 400, (B, 1), generator=g).to(dev)
+
+        def step():
+            opt.zero_grad()
+            with torch.autocast("cuda", dtype=torch.bfloat16):
+                loss = m(img, label)["loss_cls"]
+            loss.backward()
+            if world > 1:
+                ref_allreduce(m.parameters(), True, -1)
+            torch.nn.utils.clip_grad_norm_(params, max_norm=40, norm_type=2)
+            opt.step()
+
+        for _ in range(warmup):
+            step()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return world * B * steps / (ms / 1e3)
+
+    out = {"how": "unmodified reference model (baseline/_ref) on torch %s / cuDNN %s, autocast bf16, cudnn.benchmark, "
+                  "fwd+bwd+clip+SGD, %d timed steps after %d warm-ups, CUDA events, max over ranks"
+                  % (torch.__version__, torch.backends.cudnn.version(), steps, warmup)}
+    variants = {}
+    for cl in (True, False):
+        try:
+            m = build(cl)
+            variants["channels_last" if cl else "contiguous"] = (measure(m, batches[0]), m)
+        except Exception as e:
+            variants["channels_last" if cl else "contiguous"] = (0.0, None)
+            out["error_%s" % ("channels_last" if cl else "contiguous")] = repr(e)[:200]
+            torch.cuda.empty_cache()
+    best = max(variants, key=lambda k: variants[k][0])
+    out["variant"] = best
+    out["variants_B%d" % batches[0]] = {k: v[0] for k, v in variants.items()}
+    m = variants[best][1]
+    for k, v in variants.items():
+        if k != best and v[1] is not None:
+            del v
+    if m is None:
+        out["unavailable"] = "the reference model did not run on this GPU"
+        return out
+    out["B%d" % batches[0]] = variants[best][0]
+    variants.clear()
+    torch.cuda.empty_cache()
+    for B in batches[1:]:
+        try:
+            out["B%d" % B] = measure(m, B)
+        except torch.OutOfMemoryError:
+            out["B%d" % B] = None
+            out["note_B%d" % B] = "out of memory on 180 GB"
+            torch.cuda.empty_cache()
+            if world > 1:
+                break
+    return out
+
+
 # --------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -187,9 +299,13 @@ def run_ours(args):
     opt = torch.optim.SGD(model.parameters(), lr=0.015, momentum=0.9, weight_decay=1e-4, nesterov=True)
     params = [p for p in model.parameters() if p.requires_grad]
 
-    g = torch.Generator().manual_seed(1000 + rank)                 # each rank owns different clips
-    host_img = [torch.randn((B, T_FRAMES, 3, PX, PX), generator=g).pin_memory() for _ in range(2)]
-    host_lbl = [torch.randint(0, 400, (B, 1), generator=g).pin_memory() for _ in range(2)]
+    def make_batches(b, seed):
+        g = torch.Generator().manual_seed(seed + rank)             # each rank owns different clips
+        himg = [torch.randn((b, T_FRAMES, 3, PX, PX), generator=g).pin_memory() for _ in range(2)]
+        hlbl = [torch.randint(0, 400, (b, 1), generator=g).pin_memory() for _ in range(2)]
+        return himg, hlbl
+
+    host_img, host_lbl = make_batches(B, 1000)
     dev_img = [h.to(dev) for h in host_img]
     dev_lbl = [h.to(dev) for h in host_lbl]
 
@@ -217,7 +333,18 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- resident-input timing (value) + live MVF kernel timing (roofline)
+    def timed(imgs, lbls, n):
+        """n steps between two CUDA events on the compute stream, barrier + synchronize on both sides, max over ranks."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            train_step(imgs[i % 2], lbls[i % 2])
+        e1.record()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- resident-input timing (value) + live per-family kernel timing (roofline, roofline_by_family)
     for i in range(args.warmup):
         train_step(dev_img[i % 2], dev_lbl[i % 2])
     barrier()
@@ -226,13 +353,7 @@ def run_ours(args):
         sampler.start()
     launches0 = _lib.launch_count()
     mvf_mod.timing_begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        train_step(dev_img[i % 2], dev_lbl[i % 2])
-    e1.record()
-    barrier()
-    ms = max_over_ranks(e0.elapsed_time(e1))
+    ms = timed(dev_img, dev_lbl, args.steps)
     launches = _lib.launch_count() - launches0
     timing = mvf_mod.timing_end()
     clocks = sampler.stop() if rank == 0 else None
@@ -284,38 +405,83 @@ def run_ours(args):
     ms_e2e = max_over_ranks(t0.elapsed_time(t1))
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
     h2d = host_img[0].numel() * 4 + host_lbl[0].numel() * 8
+    peak_gb = round(torch.cuda.max_memory_allocated(dev) / 2**30, 1)
+    del slots_img, slots_lbl, dev_img, dev_lbl, host_img, host_lbl
+
+    # ---- batch sweep of OUR arm (resident inputs): the reference recipe's B = 12 (r50_dense.py:122) and B = 64
+    sweep = {"B%d" % B: value}
+    for b in [int(v) for v in args.sweep.split(",") if v]:
+        if b == B:
+            continue
+        himg, hlbl = make_batches(b, 3000)
+        dimg, dlbl = [h.to(dev) for h in himg], [h.to(dev) for h in hlbl]
+        for i in range(3):
+            train_step(dimg[i % 2], dlbl[i % 2])
+        n = max(6, min(args.steps, 20))
+        sweep["B%d" % b] = world * b * n / (timed(dimg, dlbl, n) / 1e3)
+        del himg, hlbl, dimg, dlbl
+
+    # ---- the GPU bar: the unmodified reference on PyTorch / cuDNN on the same GPU(s), same run
+    bar = None
+    if not args.no_gpu_bar:
+        import gc
+        del model, opt, flat, params
+        gc.collect()
+        torch.cuda.empty_cache()
+        bar = gpu_bar(dev, world, rank, [12, 64] + ([B] if B not in (12, 64) else []))
+        if "B%d" % B in bar and bar.get("B%d" % B):
+            bar["ratio_equal_B"] = value / bar["B%d" % B]
+        for b in (12, 64):
+            if bar.get("B%d" % b) and sweep.get("B%d" % b):
+                bar["ratio_B%d" % b] = sweep["B%d" % b] / bar["B%d" % b]
+        best_ref = max([v for k, v in bar.items() if k.startswith("B") and isinstance(v, float)], default=None)
+        if best_ref:
+            bar["value"], bar["unit"] = best_ref, "clips/s"
+            bar["ratio"] = value / best_ref                         # our headline over the reference's best batch size
 
     if rank != 0:
         return
-    # ---- roofline of the dominant hot-path kernel (fused MVF forward), HBM-bound
+    # ---- roofline of the hot-path kernel the north star names (fused MVF forward), HBM-bound, and of every family
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak_tf, peak_src = 1400.0, "fallback 6.65 TB/s / 1.4 PFLOP/s sustained (B200_PROFILING.md)"
+    peak = 6650.0
     if os.path.exists(peaks_path):
-        peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (burst copy)"
-    else:
-        peak, peak_src = 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
-    fwd = [(b, s.elapsed_time(e)) for k, b, s, e in timing if k == "mvf_fwd"]
-    bwd = [(b, s.elapsed_time(e)) for k, b, s, e in timing if k == "mvf_bwd"]
-
-    def agg(rows):
-        if not rows:
-            return None, None, 0
-        tot_b, tot_ms = sum(r[0] for r in rows), sum(r[1] for r in rows)
-        return tot_b / (tot_ms * 1e-3) / 1e9, tot_ms / len(rows) * 1e3, len(rows)
-
-    a_f, us_f, n_f = agg(fwd)
-    a_b, us_b, n_b = agg(bwd)
+        pk = json.load(open(peaks_path))
+        peak, peak_tf = float(pk["hbm_gbs"]), float(pk.get("bf16_tflops_sustained", 1400.0))
+        peak_src = "MEASURED_PEAKS.json hbm_gbs (burst copy) / bf16_tflops_sustained"
+    fams = {}
+    for kind, nbytes, s0, s1, flops in timing:
+        f = fams.setdefault(kind, [0, 0.0, 0.0, 0.0])
+        f[0] += 1
+        f[1] += s0.elapsed_time(s1)
+        f[2] += nbytes
+        f[3] += flops
+    by_family, timed_ms = {}, 0.0
+    for kind, (cnt, fms, nbytes, flops) in sorted(fams.items(), key=lambda kv: -kv[1][1]):
+        gbs = nbytes / (fms * 1e-3) / 1e9
+        row = {"launches_per_step": cnt / args.steps, "ms_per_step": fms / args.steps,
+               "share_of_step": fms / ms, "achieved_gbs": gbs, "frac_hbm": gbs / peak}
+        if flops:
+            tf = flops / (fms * 1e-3) / 1e12
+            row["achieved_tflops"], row["frac_tensor"] = tf, tf / peak_tf
+        by_family[kind] = row
+        timed_ms += fms
+    by_family["other (ATen / NCCL / gaps, not bracketed)"] = {"ms_per_step": (ms - timed_ms) / args.steps,
+                                                              "share_of_step": 1.0 - timed_ms / ms}
+    f_fwd, f_bwd = fams.get("mvf_fwd"), fams.get("mvf_bwd")
+    a_f = f_fwd[2] / (f_fwd[1] * 1e-3) / 1e9 if f_fwd else None
+    a_b = f_bwd[2] / (f_bwd[1] * 1e-3) / 1e9 if f_bwd else None
     roofline = {"bound": "hbm", "kernel": "mvf_fwd = mvf_sweep_kernel (fused T/H/W stencil + train-mode BN3d + hardswish, one cooperative launch)", "achieved": a_f,
                 "peak": peak, "unit": "GB/s", "frac": (a_f / peak) if a_f else None,
-                # ncu --set full (profiles/r01_mvf_v4_sweep_ncu_full.csv, train-mode launch, 14x14 slab, 128 clips):
-                # dram read 53.1 MB + write 6.0 MB per launch against 102.8 MB algorithmic -- x is read once (the second
-                # sweep is served by L2) and most of the result slab is still dirty in L2 when the kernel ends, the
-                # consumer GEMM reads it from there.  Scaled to this run's mean launch.
-                "traffic": (0.575 * sum(r[0] for r in fwd) / len(fwd)) if fwd else None,
-                "peak_source": peak_src, "launches_timed": n_f, "avg_launch_us": us_f,
+                "traffic": MVF_FWD_TRAFFIC_RATIO * f_fwd[2] / f_fwd[0] if (f_fwd and MVF_FWD_TRAFFIC_RATIO) else None,
+                "traffic_source": MVF_FWD_TRAFFIC_SOURCE,
+                "peak_source": peak_src, "launches_timed": f_fwd[0] if f_fwd else 0,
+                "avg_launch_us": f_fwd[1] / f_fwd[0] * 1e3 if f_fwd else None,
                 "algorithmic_bytes": "2*E*s per launch (E = B*T*Cs*H*W slab elements, s = 2 B bf16), summed over "
                                      "the 9 MVF modules of R50",
-                "mvf_bwd": {"achieved": a_b, "frac": (a_b / peak) if a_b else None, "avg_launch_us": us_b,
-                            "launches_timed": n_b, "algorithmic_bytes": "3*E*s"}}
+                "mvf_bwd": {"achieved": a_b, "frac": (a_b / peak) if a_b else None,
+                            "avg_launch_us": f_bwd[1] / f_bwd[0] * 1e3 if f_bwd else None,
+                            "launches_timed": f_bwd[0] if f_bwd else 0, "algorithmic_bytes": "3*E*s"}}
     cpu = cpu_baseline(args.cpu_seconds) if world == 1 else None
     line = {"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -325,10 +491,13 @@ def run_ours(args):
                                    " (BASELINE.json configs[1])" if (DEPTH, T_FRAMES) == (50, 8) else ""),
                        "clips_per_gpu": B, "frames_per_gpu": B * T_FRAMES, "parallelism": "dp%d" % world,
                        "l2": "no flush: one step streams >10 GB of activations, far above the 126 MB L2",
-                       "peak_hbm_gb": round(torch.cuda.max_memory_allocated(dev) / 2**30, 1)},
+                       "peak_hbm_gb": peak_gb},
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline}
+            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_by_family": by_family,
+            "sweep": sweep}
+    if bar is not None:
+        line["gpu_bar"] = bar
     if (DEPTH, T_FRAMES) == (50, 8):
         # per-layer max(tensor time, min HBM traffic time) bound of the conv stack, fwd+bwd
         bound = 4680.0 * world
@@ -351,6 +520,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--depth", type=int, default=DEPTH, help="ResNet depth (50: BASELINE configs[1]; 101: configs[3])")
     ap.add_argument("--frames", type=int, default=T_FRAMES, help="frames per clip T (8: configs[1]; 16: configs[2])")
+    ap.add_argument("--sweep", default="12,64", help="extra clips-per-GPU sizes our arm is also timed at (resident inputs)")
+    ap.add_argument("--no-gpu-bar", action="store_true", help="skip the reference-on-PyTorch/cuDNN arm (gpu_bar)")
     ap.add_argument("--kernels-only", action="store_true",
                     help="profiling runs (ncu): skip the e2e loop and the cpu_baseline sample")
     args = ap.parse_args()

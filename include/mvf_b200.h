@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define MVFB_VERSION 100
+#define MVFB_VERSION 200
 
 enum { MVFB_OK = 0, MVFB_ERR_ARG = 1, MVFB_ERR_CUDA = 2, MVFB_ERR_UNSUPPORTED = 3, MVFB_ERR_WORKSPACE = 4 };
 enum { MVFB_F32 = 0, MVFB_BF16 = 1 };
@@ -41,6 +41,19 @@ int mvf_b200_version(void);
 const char* mvf_b200_last_error(void);
 /* Number of kernels launched by this library in this process so far (bench.py `gpu_launches`). */
 unsigned long long mvf_b200_launch_count(void);
+/* Kernel tier that served the last successful mvf_fwd / mvf_bwd call of the calling thread: "sweep" (persistent
+ * frame-stream kernels on the bf16-operand FMA, mvf_sweep.cu / mvf_sweep_bwd.cu), "stream" (mvf_stream*.cu), "ring"
+ * (mvf_fast.cu) or "generic" (any layout / dtype, mvf_generic.cu); "" before the first call.  The parity tests assert
+ * it, so a silent fall-through to a slower tier fails them. */
+const char* mvf_b200_last_kernel(void);
+/* Test / tool switches (process-wide; nothing in the library reads the environment).
+ *   MVFB_OPT_FORCE_FWD / MVFB_OPT_FORCE_BWD: 0 = automatic tier selection (default), else one of MVFB_KERNEL_*: only
+ *       that tier may serve mvf_fwd / mvf_bwd -- a descriptor it cannot serve fails with MVFB_ERR_UNSUPPORTED;
+ *   MVFB_OPT_SWEEP_DEBUG: 1 = the sweep forward kernel writes %globaltimer stamps at workspace + 512 KiB (needs a
+ *       workspace of >= 1 MiB; tools/stream_timeline.py). */
+enum { MVFB_OPT_FORCE_FWD = 0, MVFB_OPT_FORCE_BWD = 1, MVFB_OPT_SWEEP_DEBUG = 2 };
+enum { MVFB_KERNEL_AUTO = 0, MVFB_KERNEL_SWEEP = 1, MVFB_KERNEL_STREAM = 2, MVFB_KERNEL_RING = 3, MVFB_KERNEL_GENERIC = 4 };
+int mvf_b200_set_option(int key, int value);
 
 /* ------------------------------------------------------------------------------------------------
  * MVF module  --  replaces MVF.forward up to (not including) self.net: the view/transpose/split,
@@ -59,6 +72,12 @@ typedef struct {
   int training;           /* 1: batch statistics + running-stat update; 0: running statistics        */
   float eps, momentum;    /* BatchNorm3d defaults 1e-5, 0.1                                          */
 } mvfb_mvf_desc;
+
+/* Kernel tier that mvf_fwd (backward = 0) / mvf_bwd (backward = 1) selects for this descriptor from its shape alone
+ * ("" for an invalid descriptor); host-only, needs no GPU.  A call can still step down a tier at run time (pointers
+ * or strides that are not 16-byte aligned, a cooperative launch the device cannot co-schedule): mvf_b200_last_kernel()
+ * tells what actually ran. */
+const char* mvf_b200_plan(const mvfb_mvf_desc* d, int backward);
 
 /* Bytes of scratch `workspace` the forward / backward need for this descriptor. */
 size_t mvf_fwd_workspace_bytes(const mvfb_mvf_desc* d);

@@ -14,6 +14,9 @@ LIB_PATH = os.path.join(HERE, "libmvf_b200.so")
 MVFB_F32, MVFB_BF16 = 0, 1
 MVFB_NCHW, MVFB_NHWC = 0, 1
 MODES = {"T": 0, "TH": 1, "THW": 2}
+# mvf_b200_set_option keys / kernel tiers (include/mvf_b200.h)
+OPT_FORCE_FWD, OPT_FORCE_BWD, OPT_SWEEP_DEBUG = 0, 1, 2
+KERNELS = {"auto": 0, "sweep": 1, "stream": 2, "ring": 3, "generic": 4}
 
 
 class MvfDesc(C.Structure):
@@ -41,14 +44,11 @@ def _declare(l):
     l.mvf_bwd.restype = C.c_int
     l.mvf_bwd.argtypes = [C.POINTER(MvfDesc), _VP, _LL, _VP, _VP, _LL, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP,
                           _FP, _FP, _FP, _FP, _FP, _VP, _SZ, _VP]
-    for name, sig in _OPTIONAL.items():
-        fn = getattr(l, name, None)
-        if fn is not None:
-            fn.restype, fn.argtypes = sig
-
-
-# entry points added after the first milestone; declared lazily so an older .so still loads for the MVF path
-_OPTIONAL = {}
+    l.mvf_b200_last_kernel.restype = C.c_char_p
+    l.mvf_b200_plan.restype = C.c_char_p
+    l.mvf_b200_plan.argtypes = [C.POINTER(MvfDesc), C.c_int]
+    l.mvf_b200_set_option.restype = C.c_int
+    l.mvf_b200_set_option.argtypes = [C.c_int, C.c_int]
 
 
 def lib():
@@ -77,6 +77,37 @@ def check(rc, what=""):
 
 def launch_count() -> int:
     return int(lib().mvf_b200_launch_count())
+
+
+def last_kernel() -> str:
+    """Kernel tier ("sweep" / "stream" / "ring" / "generic") that served this thread's last mvf_fwd / mvf_bwd."""
+    return lib().mvf_b200_last_kernel().decode()
+
+
+def plan(desc, backward=False) -> str:
+    """Tier mvf_fwd / mvf_bwd selects for a descriptor from its shape alone (host-only)."""
+    return lib().mvf_b200_plan(C.byref(desc), int(backward)).decode()
+
+
+def set_option(key: int, value: int) -> None:
+    check(lib().mvf_b200_set_option(key, value), "mvf_b200_set_option")
+
+
+class force_kernel:
+    """Context manager for tests / tools: only the named tier may serve mvf_fwd (`fwd=`) / mvf_bwd (`bwd=`)."""
+
+    def __init__(self, fwd="auto", bwd="auto"):
+        self.fwd, self.bwd = KERNELS[fwd], KERNELS[bwd]
+
+    def __enter__(self):
+        set_option(OPT_FORCE_FWD, self.fwd)
+        set_option(OPT_FORCE_BWD, self.bwd)
+        return self
+
+    def __exit__(self, *exc):
+        set_option(OPT_FORCE_FWD, 0)
+        set_option(OPT_FORCE_BWD, 0)
+        return False
 
 
 def ptr(t):

@@ -25,14 +25,23 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 int num_sms() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  static std::atomic<int> sms[64];                      // per device: a process may drive several GPUs
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  std::atomic<int>& slot = sms[dev & 63];
+  int n = slot.load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    slot.store(n, std::memory_order_relaxed);
   }
-  return sms;
+  return n;
 }
+
+static thread_local const char* g_last_kernel = "";
+void note_kernel(const char* name) { g_last_kernel = name; }
+
+static std::atomic<int> g_options[OPT_COUNT];
+int option(int key) { return key >= 0 && key < OPT_COUNT ? g_options[key].load(std::memory_order_relaxed) : 0; }
 
 static PFN_cuTensorMapEncodeTiled_v12000 get_encode_tiled() {
   static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
@@ -112,6 +121,26 @@ extern "C" {
 int mvf_b200_version(void) { return MVFB_VERSION; }
 const char* mvf_b200_last_error(void) { return g_err; }
 unsigned long long mvf_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+const char* mvf_b200_last_kernel(void) { return g_last_kernel; }
+const char* mvf_b200_plan(const mvfb_mvf_desc* d, int backward) {
+  if (check_mvf_desc(d)) return "";
+  const int force = option(backward ? OPT_FORCE_BWD : OPT_FORCE_FWD);
+  const auto on = [&](int k) { return force == 0 || force == k; };
+  if (!backward) {
+    if (on(MVFB_KERNEL_SWEEP) && mvf_sweep_supported(d)) return "sweep";
+    if (on(MVFB_KERNEL_STREAM) && mvf_stream_supported(d)) return "stream";
+    if (on(MVFB_KERNEL_RING) && mvf_fast_supported(d)) return "ring";
+  } else {
+    if (on(MVFB_KERNEL_STREAM) && mvf_stream_bwd_supported(d)) return "stream";
+    if (on(MVFB_KERNEL_RING) && mvf_fast_bwd_supported(d)) return "ring";
+  }
+  return on(MVFB_KERNEL_GENERIC) ? "generic" : "";
+}
+int mvf_b200_set_option(int key, int value) {
+  MVFB_CHECK(key >= 0 && key < OPT_COUNT, MVFB_ERR_ARG, "unknown option %d", key);
+  g_options[key].store(value, std::memory_order_relaxed);
+  return MVFB_OK;
+}
 
 size_t mvf_fwd_workspace_bytes(const mvfb_mvf_desc* d) {
   if (!d) return 0;
@@ -151,24 +180,33 @@ int mvf_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_stride, 
   MVFB_CHECK(workspace_bytes >= mvf_fwd_workspace_bytes(d) && workspace, MVFB_ERR_WORKSPACE,
              "workspace too small: %zu < %zu", workspace_bytes, mvf_fwd_workspace_bytes(d));
   cudaStream_t st = (cudaStream_t)stream;
-  static const char* prefer = getenv("MVFB_FWD");             // tuning experiments: "stream" / "ring" skip newer kernels
-  if (!prefer && mvf_sweep_supported(d)) {
+  // Kernel tiers, fastest first; each declines (MVFB_ERR_UNSUPPORTED) what it cannot serve.  `force` pins one tier
+  // (tests and tools only, mvf_b200_set_option): a forced tier that declines is an error, not a fall-through.
+  const int force = option(OPT_FORCE_FWD);
+  if ((force == 0 || force == MVFB_KERNEL_SWEEP) && mvf_sweep_supported(d)) {
     rc = mvf_sweep_fwd(d, x, y, y_stride, wt, wh, ww, gamma, beta, running_mean, running_var, save_mean, save_rstd,
-                       workspace, st);
+                       workspace, workspace_bytes, st);
+    if (rc == MVFB_OK) note_kernel("sweep");
     if (rc != MVFB_ERR_UNSUPPORTED) return rc;
   }
-  if (!(prefer && prefer[0] == 'r') && mvf_stream_supported(d)) {
+  if ((force == 0 || force == MVFB_KERNEL_STREAM) && mvf_stream_supported(d)) {
     rc = mvf_stream_fwd(d, x, y, y_stride, wt, wh, ww, gamma, beta, running_mean, running_var, save_mean, save_rstd,
                         workspace, st);
+    if (rc == MVFB_OK) note_kernel("stream");
     if (rc != MVFB_ERR_UNSUPPORTED) return rc;
   }
-  if (mvf_fast_supported(d)) {
+  if ((force == 0 || force == MVFB_KERNEL_RING) && mvf_fast_supported(d)) {
     rc = mvf_fast_fwd(d, x, y, y_stride, wt, wh, ww, gamma, beta, running_mean, running_var, save_mean, save_rstd,
                       workspace, st);
+    if (rc == MVFB_OK) note_kernel("ring");
     if (rc != MVFB_ERR_UNSUPPORTED) return rc;   // unaligned pointers / strides: take the layout-generic kernels
   }
-  return mvf_generic_fwd(d, x, y, y_stride, wt, wh, ww, gamma, beta, running_mean, running_var, save_mean, save_rstd,
-                         workspace, st);
+  MVFB_CHECK(force == 0 || force == MVFB_KERNEL_GENERIC, MVFB_ERR_UNSUPPORTED,
+             "forced forward kernel tier %d does not serve this descriptor", force);
+  rc = mvf_generic_fwd(d, x, y, y_stride, wt, wh, ww, gamma, beta, running_mean, running_var, save_mean, save_rstd,
+                       workspace, st);
+  if (rc == MVFB_OK) note_kernel("generic");
+  return rc;
 }
 
 int mvf_bwd(const mvfb_mvf_desc* d, const void* g, long long g_stride, const void* x, void* dx, long long dx_stride,
@@ -211,18 +249,25 @@ int mvf_bwd(const mvfb_mvf_desc* d, const void* g, long long g_stride, const voi
     }
   }
   ws += 2 * sizeof(float) * (((size_t)d->Cs + 63) / 64 * 64);
-  if (mvf_stream_bwd_supported(d)) {
+  const int force = option(OPT_FORCE_BWD);
+  if ((force == 0 || force == MVFB_KERNEL_STREAM) && mvf_stream_bwd_supported(d)) {
     rc = mvf_stream_bwd(d, g, g_stride, x, dx, dx_stride, wt, wh, ww, gamma, beta, mean, rstd, dwt, dwh, dww, dgamma,
                         dbeta, ws, st);
+    if (rc == MVFB_OK) note_kernel("stream");
     if (rc != MVFB_ERR_UNSUPPORTED) return rc;
   }
-  if (mvf_fast_bwd_supported(d)) {
+  if ((force == 0 || force == MVFB_KERNEL_RING) && mvf_fast_bwd_supported(d)) {
     rc = mvf_fast_bwd(d, g, g_stride, x, dx, dx_stride, wt, wh, ww, gamma, beta, mean, rstd, dwt, dwh, dww, dgamma,
                       dbeta, ws, st);
+    if (rc == MVFB_OK) note_kernel("ring");
     if (rc != MVFB_ERR_UNSUPPORTED) return rc;
   }
-  return mvf_generic_bwd(d, g, g_stride, x, dx, dx_stride, wt, wh, ww, gamma, beta, mean, rstd, dwt, dwh, dww, dgamma,
-                         dbeta, ws, st);
+  MVFB_CHECK(force == 0 || force == MVFB_KERNEL_GENERIC, MVFB_ERR_UNSUPPORTED,
+             "forced backward kernel tier %d does not serve this descriptor", force);
+  rc = mvf_generic_bwd(d, g, g_stride, x, dx, dx_stride, wt, wh, ww, gamma, beta, mean, rstd, dwt, dwh, dww, dgamma,
+                       dbeta, ws, st);
+  if (rc == MVFB_OK) note_kernel("generic");
+  return rc;
 }
 
 }  // extern "C"

@@ -409,11 +409,11 @@ int bn_stats(const mvfb_bn_desc* d, const void* x, long long ldx, float* sums, m
   cudaStream_t st = (cudaStream_t)stream;
   MVFB_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * d->C, st));
   const size_t sm = scratch_bytes(d->C);
-  static bool once = false;
-  if (!once) {
+  static DevOnce once;
+  if (once.pending()) {
     MVFB_CUDA(cudaFuncSetAttribute(bn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
     MVFB_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<kRowsPerIter>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    once = true;
+    once.done();
   }
   bn_stats_kernel<<<grid_for(d->M, d->C), kThreads, sm, st>>>((const __nv_bfloat16*)x, ldx, d->M, d->C, sums);
   count_launch();
@@ -461,10 +461,10 @@ int bn_bwd(const mvfb_bn_desc* d, const void* g, long long ldg, const void* y, l
   a.gamma = gamma; a.mean = mean; a.rstd = rstd; a.sums = sums; a.dgamma = dgamma; a.dbeta = dbeta;
   MVFB_CHECK(!d->relu || y || relu_mask, MVFB_ERR_ARG, "relu backward needs the forward output y or its bit mask");
   MVFB_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * d->C, st));
-  static bool once = false;
-  if (!once) {
+  static DevOnce once;
+  if (once.pending()) {
     MVFB_CUDA(cudaFuncSetAttribute(bn_bwd_reduce_kernel<kRowsPerIter>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    once = true;
+    once.done();
   }
   const int grid = grid_for(d->M, d->C);
   bn_bwd_reduce_kernel<kRowsPerIter><<<grid, kThreads, scratch_bytes(d->C), st>>>(a);

@@ -287,10 +287,10 @@ int launch_kernel(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtens
   using C = Cfg<BN>;
   a.m_tiles = (int)((a.M + BM - 1) / BM);
   a.n_tiles = a.N / BN;
-  static bool once = false;
-  if (!once) {
+  static DevOnce once;
+  if (once.pending()) {
     MVFB_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
-    once = true;
+    once.done();
   }
   int grid = a.m_tiles * a.n_tiles;
   if (grid > num_sms()) grid = num_sms();

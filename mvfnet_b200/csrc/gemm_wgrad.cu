@@ -202,10 +202,10 @@ int launch_wgrad_kernel(const CUtensorMap& tmG, const CUtensorMap& tmX0, const C
   if (splits > a.pblocks) splits = a.pblocks;
   if (splits < 1) splits = 1;
   a.splits = splits;
-  static bool once = false;
-  if (!once) {
+  static DevOnce once;
+  if (once.pending()) {
     MVFB_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel<BN, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
-    once = true;
+    once.done();
   }
   MVFB_CUDA(cudaMemsetAsync(a.dw, 0, sizeof(float) * dw_elems, st));
   gemm_wgrad_kernel<BN, IM2COL><<<tiles * splits, kThreads, C::kSmem, st>>>(tmG, tmX0, tmX1, a);

@@ -991,18 +991,16 @@ static bool choose_resident(const mvfb_mvf_desc* d, Geo& out, size_t& smem) {
   const int want = 2 * num_sms();
   const int cands[4] = {64, 32, 16, 8};
   bool found = false;
-  static const int forced = getenv("MVFB_CG") ? atoi(getenv("MVFB_CG")) : 0;   // tuning experiments only
   for (int i = 0; i < 4; ++i) {
     const int Cg = cands[i];
     if (d->Cs % Cg) continue;
-    if (forced && Cg != forced) continue;
     if (Cg == 8 && found) break;
     Geo g;
     fill_geo(g, d, Cg, d->T);
     const int G = Cg / 8;
     const size_t need = 256 + (size_t)d->T * g.slot_x + 2 * Cg * 4 + (size_t)kWarps * G * 16 * 4 + G * 16 * 4 + 3 * kThreads * 8;
     if (need > (size_t)kSmemLimit) continue;
-    if (need > 112 * 1024 && Cg > 16 && !forced) continue;
+    if (need > 112 * 1024 && Cg > 16) continue;
     out = g;
     smem = need;
     found = true;
@@ -1014,13 +1012,13 @@ static bool choose_resident(const mvfb_mvf_desc* d, Geo& out, size_t& smem) {
 template <int T>
 static int launch_resident(const mvfb_mvf_desc* d, const CUtensorMap& tmx, const FwdArgs& a, size_t smem,
                            cudaStream_t st) {
-  static bool once = false;
+  static DevOnce once;
   int rc;
-  if (!once) {
+  if (once.pending()) {
     if ((rc = set_smem(mvf_fwd_resident_kernel<PASS_STATS, T>, kSmemLimit))) return rc;
     if ((rc = set_smem(mvf_fwd_resident_kernel<PASS_TRAIN, T>, kSmemLimit))) return rc;
     if ((rc = set_smem(mvf_fwd_resident_kernel<PASS_APPLY, T>, kSmemLimit))) return rc;
-    once = true;
+    once.done();
   }
   const dim3 grid(d->N * (d->Cs / a.g.Cg));
   if (d->use_hs && d->training) {
@@ -1063,11 +1061,11 @@ int mvf_fast_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_str
   const size_t smem = fwd_smem(g);
   const dim3 grid(d->N * (d->Cs / g.Cg));
   if (d->use_hs && d->training) {
-    static bool once = false;
-    if (!once) {
+    static DevOnce once;
+    if (once.pending()) {
       if ((rc = set_smem(mvf_fast_fwd_kernel<PASS_STATS>, kSmemLimit))) return rc;
       if ((rc = set_smem(mvf_fast_fwd_kernel<PASS_TRAIN>, kSmemLimit))) return rc;
-      once = true;
+      once.done();
     }
     mvf_fast_fwd_kernel<PASS_STATS><<<grid, kThreads, smem, st>>>(tmx, a);
     count_launch();
@@ -1076,10 +1074,10 @@ int mvf_fast_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_str
     count_launch();
     MVFB_LAUNCH_CHECK();
   } else {
-    static bool once = false;
-    if (!once) {
+    static DevOnce once;
+    if (once.pending()) {
       if ((rc = set_smem(mvf_fast_fwd_kernel<PASS_APPLY>, kSmemLimit))) return rc;
-      once = true;
+      once.done();
     }
     mvf_fast_fwd_kernel<PASS_APPLY><<<grid, kThreads, smem, st>>>(tmx, a);
     count_launch();
@@ -1111,11 +1109,11 @@ int mvf_fast_bwd(const mvfb_mvf_desc* d, const void* gp, long long g_stride, con
   a.dwt = dwt; a.dwh = (has_h && !a.share_h) ? dwh : nullptr; a.dww = (has_w && !a.share_w) ? dww : nullptr;
   a.dgamma = dgamma; a.dbeta = dbeta;
   a.dx = (__nv_bfloat16*)dx; a.dx_pix = dx_stride;
-  static bool once = false;
-  if (!once) {
+  static DevOnce once;
+  if (once.pending()) {
     if ((rc = set_smem(mvf_fast_bwd_reduce_kernel, kSmemLimit))) return rc;
     if ((rc = set_smem(mvf_fast_bwd_dx_kernel, kSmemLimit))) return rc;
-    once = true;
+    once.done();
   }
   const dim3 grid(d->N * (d->Cs / g.Cg));
   if (d->use_hs) {

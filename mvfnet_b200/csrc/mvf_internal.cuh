@@ -45,7 +45,7 @@ bool mvf_sweep_supported(const mvfb_mvf_desc* d);
 size_t mvf_sweep_ws(const mvfb_mvf_desc* d);
 int mvf_sweep_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_stride, const float* wt,
                   const float* wh, const float* ww, const float* gamma, const float* beta, float* rm, float* rv,
-                  float* save_mean, float* save_rstd, void* ws, cudaStream_t st);
+                  float* save_mean, float* save_rstd, void* ws, size_t ws_bytes, cudaStream_t st);
 
 // ---- mvf_stream_bwd.cu : bf16 NHWC backward, persistent frame stream (preferred backward path, whole-frame tiles)
 bool mvf_stream_bwd_supported(const mvfb_mvf_desc* d);

@@ -560,9 +560,8 @@ int make_map(CUtensorMap* tm, const void* base, long long pix_stride, const BGeo
 }  // namespace
 
 bool mvf_stream_bwd_supported(const mvfb_mvf_desc* d) {
-  static const bool off = getenv("MVFB_BWD") && getenv("MVFB_BWD")[0] == 'r';   // "ring": tuning experiments
   BGeo ga, gb;
-  return !off && choose_bwd(d, 8, false, ga) && choose_bwd(d, VB, true, gb);
+  return choose_bwd(d, 8, false, ga) && choose_bwd(d, VB, true, gb);
 }
 
 size_t mvf_stream_bwd_ws(const mvfb_mvf_desc* d) {
@@ -597,11 +596,11 @@ int mvf_stream_bwd(const mvfb_mvf_desc* d, const void* gp, long long g_stride, c
   a.dwt = dwt; a.dwh = (has_h && !a.share_h) ? dwh : nullptr; a.dww = (has_w && !a.share_w) ? dww : nullptr;
   a.dgamma = dgamma; a.dbeta = dbeta;
   a.dx = (__nv_bfloat16*)dx; a.dx_pix = dx_stride;
-  static bool once = false;
-  if (!once) {
+  static DevOnce once;
+  if (once.pending()) {
     MVFB_CUDA(cudaFuncSetAttribute(mvf_stream_bwd_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
     MVFB_CUDA(cudaFuncSetAttribute(mvf_stream_bwd_dx, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    once = true;
+    once.done();
   }
   const dim3 grid(g.ngroups * g.P);
   if (d->use_hs) {

@@ -76,7 +76,10 @@ struct SwArgs {
   const float *wt, *wh, *ww, *gamma, *beta;
   float *running_mean, *running_var, *save_mean, *save_rstd;
   uint2* partials;        // [grid][2*Cg] {fp32 partial sum, epoch}
-  unsigned int epoch;     // unique per train-mode launch: tags the partials of THIS launch
+  unsigned int* epochs;   // [ngroups] device-resident launch tags, one per channel group: every CTA of the group reads
+                          // the word, tags its partials with it, and the group's first CTA increments it once the
+                          // exchange has completed.  The tag therefore changes from launch to launch without any host
+                          // state: a CUDA-graph replay of the launch is as safe as the launch itself.
   int pre_frames;         // sweep-1 frames requested before the grid exchange has completed
   __nv_bfloat16* y;
   long long y_pix;
@@ -114,13 +117,17 @@ __device__ __forceinline__ void fh8(float2 (&z)[4], const P8& x, const P8& k) {
 #pragma unroll
   for (int j = 0; j < 4; ++j) fh2(z[j], x.v[j], k.v[j]);
 }
+// {fp32 value, epoch} travels as ONE 64-bit scalar access: single-copy atomic in the PTX memory model (a .v2.u32
+// vector access is two independent 32-bit accesses as far as the model is concerned, so a reader could pair the new
+// epoch with a stale value half).
 __device__ __forceinline__ uint2 ld_relaxed_v2(const uint2* p) {
-  uint2 v;
-  asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
-  return v;
+  unsigned long long w;
+  asm volatile("ld.relaxed.gpu.global.b64 %0, [%1];" : "=l"(w) : "l"(p) : "memory");
+  return make_uint2((uint32_t)w, (uint32_t)(w >> 32));
 }
 __device__ __forceinline__ void st_relaxed_v2(uint2* p, uint2 v) {
-  asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v.x), "r"(v.y) : "memory");
+  const unsigned long long w = (unsigned long long)v.x | ((unsigned long long)v.y << 32);
+  asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(w) : "memory");
 }
 // Wait on an mbarrier phase.  The fast path is try_wait + one branch; the spin (labels are local to the PTX block)
 // gives up after ~4 s of %globaltimer so that a transfer that never lands traps instead of hanging the GPU.
@@ -181,6 +188,10 @@ mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
   const int c0 = cg * g.Cg, h0 = (tile / g.wsplit) * g.Hs, w0 = (tile % g.wsplit) * g.Ws;
   const int nclips = p < g.N ? (g.N - p + g.P - 1) / g.P : 0;
   const int KK = MODE == MODE_TRAIN ? 2 * nclips : nclips;     // clips in this CTA's stream (both sweeps)
+  unsigned int epoch = 0;                                      // train mode: this launch's tag (requested first of all)
+  // tag = word + 1, and the word is set to the tag when the exchange is over: whatever the workspace held before
+  // (zero-filled fresh memory, the rows of an earlier launch, whose tags equal the word), no stale row carries it
+  if (MODE == MODE_TRAIN) epoch = __ldcv(a.epochs + cg) + 1u;
 
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [kRing]
   uint64_t* empty = full + kRing;                               // [kRing]
@@ -498,7 +509,7 @@ mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
       if (tid < per) {                                          // row layout [vec][sum 0..7 | sumsq 0..7]
         float v = 0.f;
         for (int wv = 0; wv < g.cwarps; ++wv) v += s_red[wv * per + tid];
-        st_relaxed_v2(a.partials + (size_t)blockIdx.x * per + tid, make_uint2(__float_as_uint(v), a.epoch));
+        st_relaxed_v2(a.partials + (size_t)blockIdx.x * per + tid, make_uint2(__float_as_uint(v), epoch));
       }
       float bn_g = 1.f, bn_b = 0.f, old_rm = 0.f, old_rv = 0.f;  // gamma / beta / running statistics travel with the wait
       if (tid < g.Cg) {
@@ -520,9 +531,9 @@ mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
 #pragma unroll
               for (int u = 0; u < kBatch; ++u) {
                 const int r = r0 + u * parts;
-                v[u] = make_uint2(0u, a.epoch);
+                v[u] = make_uint2(0u, epoch);
                 if (r < rows) v[u] = ld_relaxed_v2(a.partials + ((size_t)r * g.ngroups + cg) * per + k);
-                ok = ok && v[u].y == a.epoch;
+                ok = ok && v[u].y == epoch;
               }
               if (!ok && clock64() - t0 > 4000000000LL) __trap();  // a CTA that never arrives must not hang the GPU
             } while (!ok);
@@ -557,6 +568,9 @@ mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
           }
         }
       }
+      // every CTA of this channel group has published with `epoch`, i.e. has read the word: the next launch (or the
+      // next replay of a captured graph) gets a different tag
+      if (rest == 0 && tid == 0) a.epochs[cg] = epoch;
       if (tid == 0) mbar_arrive(gate);                            // the producer may now request the rest of sweep 1
       consumer_bar_sync(nconsumer);
       load_affine();
@@ -594,17 +608,15 @@ bool choose_sweep(const mvfb_mvf_desc* d, SwGeo& g) {
   if (d->dtype != MVFB_BF16 || d->layout != MVFB_NHWC) return false;
   if (d->T != 4 && d->T != 8 && d->T != 16) return false;
   if (d->Cs % 8 != 0 || d->C % 8 != 0) return false;
-  static const bool no_rowpair = getenv("MVFB_SWEEP_RP") && getenv("MVFB_SWEEP_RP")[0] == '0';   // tuning experiments
   // 1) row-pair tiles: an even number of rows (one warp per pair, <= kCWarps) and a row of (column, vector) lanes
   //    that fits a warp.  Wide channel groups first: the TMA unit retires ~1 box row per 1.5 clocks whatever the
   //    row's size, so 64-byte rows (32 channels) halve its load per element against 32-byte rows (measured: a
   //    14x14x16-channel frame takes 0.205 us of TMA time, as long as its arithmetic).  Within a width take the
   //    tiling that loads the fewest halo pixels and idles the fewest lanes.
-  static const int only_cg = getenv("MVFB_SWEEP_CG") ? atoi(getenv("MVFB_SWEEP_CG")) : 0;                // tuning experiments
   const int cands_rp[2] = {32, 16};
-  for (int ci = 0; ci < 2 && !no_rowpair; ++ci) {
+  for (int ci = 0; ci < 2; ++ci) {
     const int Cg = cands_rp[ci];
-    if (d->Cs % Cg || (only_cg && Cg != only_cg)) continue;
+    if (d->Cs % Cg) continue;
     double best = 1e30;
     SwGeo bg;
     for (int hsplit = 1; hsplit <= d->H; ++hsplit) {
@@ -660,25 +672,17 @@ bool choose_sweep(const mvfb_mvf_desc* d, SwGeo& g) {
   return false;
 }
 
-// Epoch of a train-mode launch: tags its partial sums so that words left in the workspace by any earlier launch
-// (or uninitialised memory, with probability 2^-32 per word) are never mistaken for this launch's.
-unsigned int next_epoch() {
-  static std::atomic<unsigned int> e{0x5eed0001u};
-  return e.fetch_add(1u, std::memory_order_relaxed);
-}
-
 template <int MODE, int TT, bool RP>
 int launch_mode(const CUtensorMap& tmx, SwArgs& a, cudaStream_t st) {
-  static bool once = false;
-  if (!once) {
+  static DevOnce once;
+  if (once.pending()) {
     MVFB_CUDA(cudaFuncSetAttribute(mvf_sweep_kernel<MODE, TT, RP>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemLimit));
-    once = true;
+    once.done();
   }
   const SwGeo& g = a.g;
   const dim3 grid(g.ngroups * g.hsplit * g.wsplit * g.P), block(32 * (g.cwarps + 1));
   const size_t smem = sweep_smem(g);
   if (MODE == MODE_TRAIN) {
-    a.epoch = next_epoch();
     void* params[2] = {(void*)&tmx, (void*)&a};
     // cooperative launch: the driver guarantees that all CTAs are resident, which the grid exchange relies on
     cudaError_t e = cudaLaunchCooperativeKernel((const void*)mvf_sweep_kernel<MODE, TT, RP>, grid, block, params, smem, st);
@@ -713,6 +717,10 @@ int launch_T(const mvfb_mvf_desc* d, const CUtensorMap& tmx, SwArgs& a, cudaStre
 
 }  // namespace
 
+static size_t sweep_partial_bytes(const SwGeo& g) {
+  return ((size_t)g.ngroups * g.hsplit * g.wsplit * g.P * 2 * g.Cg * sizeof(uint2) + 255) / 256 * 256;
+}
+
 bool mvf_sweep_supported(const mvfb_mvf_desc* d) {
   SwGeo g;
   return choose_sweep(d, g);
@@ -721,12 +729,12 @@ bool mvf_sweep_supported(const mvfb_mvf_desc* d) {
 size_t mvf_sweep_ws(const mvfb_mvf_desc* d) {
   SwGeo g;
   if (!choose_sweep(d, g)) return 0;
-  return (size_t)g.ngroups * g.hsplit * g.wsplit * g.P * 2 * g.Cg * sizeof(uint2) + 256;
+  return sweep_partial_bytes(g) + (size_t)g.ngroups * sizeof(unsigned int) + 256;
 }
 
 int mvf_sweep_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_stride, const float* wt,
                   const float* wh, const float* ww, const float* gamma, const float* beta, float* rm, float* rv,
-                  float* save_mean, float* save_rstd, void* ws, cudaStream_t st) {
+                  float* save_mean, float* save_rstd, void* ws, size_t ws_bytes, cudaStream_t st) {
   SwGeo g;
   if (!choose_sweep(d, g)) return MVFB_ERR_UNSUPPORTED;
   if ((reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(y) & 15) || y_stride % 8 != 0)
@@ -748,11 +756,15 @@ int mvf_sweep_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_st
   a.gamma = gamma; a.beta = beta; a.running_mean = rm; a.running_var = rv;
   a.save_mean = save_mean; a.save_rstd = save_rstd;
   a.partials = (uint2*)ws;
-  a.epoch = 0;
-  static const int pre_frames = getenv("MVFB_SWEEP_PRE") ? atoi(getenv("MVFB_SWEEP_PRE")) : 4;   // tuning experiments
-  a.pre_frames = pre_frames < 1 ? 1 : pre_frames;   // >= 1: the last step of sweep 0 reads the first frame of sweep 1
+  a.epochs = reinterpret_cast<unsigned int*>((char*)ws + sweep_partial_bytes(g));
+  a.pre_frames = 4;   // measured best of 1..16; must be >= 1: the last step of sweep 0 reads the first frame of sweep 1
   a.y = (__nv_bfloat16*)y; a.y_pix = y_stride;
-  static const bool debug = getenv("MVFB_SWEEP_DEBUG") != nullptr;       // the tool passes a 1 MiB workspace
+  // tools/stream_timeline.py (mvf_b200_set_option(MVFB_OPT_SWEEP_DEBUG, 1)): %globaltimer stamps behind the partials
+  const bool debug = option(OPT_SWEEP_DEBUG) != 0;
+  if (debug && ws_bytes < (size_t)(1 << 20)) {
+    set_error("MVFB_OPT_SWEEP_DEBUG needs a workspace of >= 1 MiB, got %zu bytes", ws_bytes);
+    return MVFB_ERR_WORKSPACE;
+  }
   a.stamps = debug ? reinterpret_cast<unsigned long long*>((char*)ws + (512 << 10)) : nullptr;
   return g.rowpair ? launch_T<true>(d, tmx, a, st) : launch_T<false>(d, tmx, a, st);
 }

@@ -20,9 +20,10 @@ from . import _lib
 from ._lib import MvfDesc, ptr
 
 
-# Optional launch timing used by bench.py: while a list is installed here every mvf_fwd / mvf_bwd call is
-# bracketed by CUDA events recorded on the launching stream, with its algorithmic bytes (SURVEY 8d:
-# forward 2*E*s, backward 3*E*s for a slab of E elements of s bytes).
+# Optional launch timing used by bench.py: while a list is installed here every library call of the hot path is
+# bracketed by CUDA events recorded on the launching stream, with its algorithmic bytes and flops (MVF
+# forward 2*E*s, backward 3*E*s for a slab of E elements of s bytes; GEMMs 2*M*N*K flops and operand + result bytes;
+# BatchNorm kernels the bytes they stream).
 _TIMING = None
 
 
@@ -32,15 +33,16 @@ def timing_begin():
 
 
 def timing_end():
-    """-> [(kind, algorithmic_bytes, start_event, end_event)]; call after a device synchronize."""
+    """-> [(kind, algorithmic_bytes, start_event, end_event, flops)]; call after a device synchronize."""
     global _TIMING
     rec, _TIMING = _TIMING, None
     return rec or []
 
 
 class _Timed:
-    def __init__(self, kind, elems, esize):
-        self.kind, self.bytes = kind, (2 if kind == "mvf_fwd" else 3) * elems * esize
+    def __init__(self, kind, elems=0, esize=0, nbytes=None, flops=0):
+        self.kind, self.flops = kind, flops
+        self.bytes = nbytes if nbytes is not None else (2 if kind == "mvf_fwd" else 3) * elems * esize
 
     def __enter__(self):
         if _TIMING is not None:
@@ -52,7 +54,7 @@ class _Timed:
     def __exit__(self, *exc):
         if _TIMING is not None and exc[0] is None:
             self.e1.record()
-            _TIMING.append((self.kind, self.bytes, self.e0, self.e1))
+            _TIMING.append((self.kind, self.bytes, self.e0, self.e1, self.flops))
         return False
 
 

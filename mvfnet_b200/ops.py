@@ -4,13 +4,17 @@
 downsample (backbones/resnet.py:157-162,179-180,299-303) for bf16 channels_last activations;
 `mvf_conv1x1(x, mvf)` is MVF.forward as a whole (MVF.py:104-138): the fused MVF kernel writes only the compact
 slab and the GEMM reads its A operand from two tensors, so the reference's cat / contiguous copies never exist.
-Forward and input-gradient run on libmvf_b200's tcgen05 GEMM (`conv1x1_gemm`); the weight-gradient is still a
-library GEMM (torch.matmul) this round -- see DESIGN.md "gaps".
+Forward and input-gradient run on libmvf_b200's tcgen05 GEMM (`conv1x1_gemm`), the weight-gradient on its MN-major
+tcgen05 GEMM (`conv1x1_wgrad`).  3x3 convolutions, BatchNorm (+ residual + ReLU), the stem and the max-pool follow.
+
+bf16 operand forms of a weight (plain, transposed for the input-gradient, KRSC / rotated for the 3x3 kernels) are
+cached per parameter VERSION (`_wform`): one cast per optimizer step instead of one per use.
 """
 from __future__ import annotations
 
 import ctypes as C
 import os
+import weakref
 
 import torch
 
@@ -75,6 +79,45 @@ def _stream():
     return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
 
+_T = _mvf._Timed          # bench.py's per-family launch timing (no-op unless mvf.timing_begin() was called)
+
+# (id(param), form) -> (weak reference to the parameter, its version, tensor).  `Tensor._version` is bumped by every
+# in-place update (the optimizer step), so a stale form is never used, and the weak reference guards against a dead
+# parameter's id being re-used by another tensor.  Forms:
+#   "rows"  (Cout, Cin*kh*kw) bf16                     1x1 forward operand B
+#   "rowsT" (Cin, Cout) bf16                           1x1 input-gradient operand B (= W^T)
+#   "krsc"  (Cout, 3, 3, Cin) bf16                     3x3 forward operand B
+#   "rot"   (Cin, 3, 3, Cout) bf16, taps rotated 180   3x3 stride-1 input-gradient operand B
+#   "nchw"  (Cout, Cin, kh, kw) bf16                   library fallbacks
+_WFORMS = {}
+
+
+def _wform(weight, form):
+    key = (id(weight), form)
+    ver = weight._version
+    hit = _WFORMS.get(key)
+    if hit is not None and hit[0]() is weight and hit[1] == ver and hit[2].device == weight.device:
+        return hit[2]
+    w = weight.detach()
+    if form == "rows":
+        t = w.reshape(w.shape[0], -1).to(torch.bfloat16)
+    elif form == "rowsT":
+        t = _wform(weight, "rows").t().contiguous()
+    elif form == "nchw":
+        t = w.to(torch.bfloat16)
+    elif form == "krsc":
+        t = _wform(weight, "nchw").permute(0, 2, 3, 1).contiguous()
+    elif form == "rot":
+        t = _wform(weight, "nchw").flip(2, 3).permute(1, 2, 3, 0).contiguous()
+    else:
+        raise KeyError(form)
+    if len(_WFORMS) > 4096:                                    # models that came and went (test suites)
+        for k in [k for k, v in _WFORMS.items() if v[0]() is None]:
+            del _WFORMS[k]
+    _WFORMS[key] = (weakref.ref(weight), ver, t)
+    return t
+
+
 def enabled() -> bool:
     """MVFB_CONV1X1=0 routes the 1x1 convolutions back through torch / cuDNN (A/B measurements only)."""
     return os.environ.get("MVFB_CONV1X1", "1") != "0"
@@ -108,13 +151,15 @@ def gemm_tn(a1, b, a0=None, k0=0, stats=False, out=None, add=None):
     if stats:
         sums = torch.zeros((2, n), dtype=torch.float32, device=a1.device)
         colsum, colsq = sums[0], sums[1]
+    nbytes = 2 * (m * k + m * n + n * k)
     if add is not None:
         assert not stats and add.shape == (m, n) and add.stride(1) == 1 and add.dtype == torch.bfloat16
-        rc = L.conv1x1_gemm_add(C.byref(d), ptr(a0), ptr(a1), ptr(b), ptr(add), add.stride(0), ptr(out), _stream())
+        with _T("gemm1x1", nbytes=nbytes + 2 * m * n, flops=2 * m * n * k):
+            rc = L.conv1x1_gemm_add(C.byref(d), ptr(a0), ptr(a1), ptr(b), ptr(add), add.stride(0), ptr(out), _stream())
         _lib.check(rc, "conv1x1_gemm_add")
         return out, None, None
-    rc = L.conv1x1_gemm(C.byref(d), ptr(a0), ptr(a1), ptr(b), ptr(out), ptr(colsum), ptr(colsq),
-                        C.c_void_p(torch.cuda.current_stream().cuda_stream))
+    with _T("gemm1x1", nbytes=nbytes, flops=2 * m * n * k):
+        rc = L.conv1x1_gemm(C.byref(d), ptr(a0), ptr(a1), ptr(b), ptr(out), ptr(colsum), ptr(colsq), _stream())
     _lib.check(rc, "conv1x1_gemm")
     return out, colsum, colsq
 
@@ -146,7 +191,8 @@ def gemm_wgrad(g2, x1, x0=None, k0=0):
     d.M, d.N, d.K, d.K0 = m, n, k, k0
     d.lda1, d.ldb, d.ldd = x1.stride(0), g2.stride(0), k
     d.lda0 = x0.stride(0) if x0 is not None else 0
-    rc = L.conv1x1_wgrad(C.byref(d), ptr(g2), ptr(x0), ptr(x1), ptr(dw), _stream())
+    with _T("wgrad1x1", nbytes=2 * (m * n + m * k) + 4 * n * k, flops=2 * m * n * k):
+        rc = L.conv1x1_wgrad(C.byref(d), ptr(g2), ptr(x0), ptr(x1), ptr(dw), _stream())
     _lib.check(rc, "conv1x1_wgrad")
     return dw
 
@@ -163,9 +209,10 @@ class _Conv1x1(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, stats, passthrough):
         f, cin, h, w = x.shape
-        wb = weight.detach().reshape(weight.shape[0], cin).to(torch.bfloat16)
+        wb = _wform(weight, "rows")
         out, colsum, _ = gemm_tn(_rows(x), wb, stats=stats)
         ctx.save_for_backward(x, wb)
+        ctx.weight = weight
         ctx.stats, ctx.passthrough = stats, passthrough
         outs = [_nhwc_from_rows(out, f, h, w)]
         if stats:
@@ -188,7 +235,7 @@ class _Conv1x1(torch.autograd.Function):
             add = None
             if g_id is not None:
                 add = _rows(g_id.to(torch.bfloat16).contiguous(memory_format=torch.channels_last))
-            dx2, _, _ = gemm_tn(g2, wb.t().contiguous(), add=add)      # dX = dY W (+ dL/d identity)  ==  TN GEMM against W^T
+            dx2, _, _ = gemm_tn(g2, _wform(ctx.weight, "rowsT"), add=add)   # dX = dY W (+ dL/d identity)  ==  TN GEMM against W^T
             dx = _nhwc_from_rows(dx2, f, h, w)
         if ctx.needs_input_grad[1]:
             dw = gemm_wgrad(g2, _rows(x)).view(wb.shape[0], cin, 1, 1)
@@ -210,9 +257,9 @@ class _MVFConv1x1(torch.autograd.Function):
         f, c, h, w = x.shape
         slab, xk, layout, save_mean, save_rstd = _mvf.mvf_slab_forward(
             x, cfg, wt, wh, ww, gamma, beta, running_mean, running_var, out="slab")
-        wb = weight.detach().reshape(weight.shape[0], c).to(torch.bfloat16)
+        wb = _wform(weight, "rows")
         out, colsum, _ = gemm_tn(_rows(xk), wb, a0=_rows(slab), k0=cfg.Cs, stats=stats)
-        ctx.cfg, ctx.layout = cfg, layout
+        ctx.cfg, ctx.layout, ctx.weight = cfg, layout, weight
         ctx.save_for_backward(xk, slab, wb, wt, wh, ww, gamma, beta, running_mean, running_var, save_mean, save_rstd)
         y = _nhwc_from_rows(out, f, h, w)
         if not stats:
@@ -232,7 +279,7 @@ class _MVFConv1x1(torch.autograd.Function):
         g2 = _rows(g)
         # dL/dx' (all C channels) = dY W; the slab columns are then rewritten IN PLACE by mvf_bwd, which reads a
         # frame of g completely before it writes that frame's dx (kernel contract, include/mvf_b200.h)
-        dxp, _, _ = gemm_tn(g2, wb.t().contiguous())
+        dxp, _, _ = gemm_tn(g2, _wform(ctx.weight, "rowsT"))
         dw = None
         if ctx.needs_input_grad[1]:
             dw = gemm_wgrad(g2, _rows(xk), x0=_rows(slab), k0=cs).view(wb.shape[0], c, 1, 1)
@@ -282,18 +329,39 @@ def conv3x3_raw(x, w_krsc, stride, stats=False):
     d.F, d.H, d.W, d.Cin, d.Cout, d.stride, d.ksize = f, h, w, cin, cout, stride, (3 if w_krsc.dim() == 4 else 1)
     out = torch.empty((f, ho, wo, cout), dtype=torch.bfloat16, device=x.device)
     sums = torch.zeros((2, cout), dtype=torch.float32, device=x.device) if stats else None
-    rc = L.conv3x3_gemm(C.byref(d), ptr(x), ptr(w_krsc), ptr(out), ptr(sums[0]) if stats else None,
-                        ptr(sums[1]) if stats else None, _stream())
+    taps = 9 if w_krsc.dim() == 4 else 1
+    mo = f * ho * wo
+    with _T("conv3x3" if taps == 9 else "gemm1x1", nbytes=2 * (f * h * w * cin // (1 if taps == 9 else stride * stride)
+                                                             + mo * cout + taps * cin * cout),
+            flops=2 * mo * cout * taps * cin):
+        rc = L.conv3x3_gemm(C.byref(d), ptr(x), ptr(w_krsc), ptr(out), ptr(sums[0]) if stats else None,
+                            ptr(sums[1]) if stats else None, _stream())
     _lib.check(rc, "conv3x3_gemm")
     return out.permute(0, 3, 1, 2), sums
+
+
+def conv3x3_wgrad_raw(g, x, cout, stride, ksize):
+    """dW of the 3x3 (ksize 3 -> (Cout, 3, 3, Cin) fp32) or strided 1x1 (ksize 1 -> (Cout, Cin)) convolution."""
+    f, cin, h, w = x.shape
+    d = ConvDesc()
+    d.F, d.H, d.W, d.Cin, d.Cout, d.stride, d.ksize = f, h, w, cin, cout, stride, ksize
+    shape = (cout, 3, 3, cin) if ksize == 3 else (cout, cin)
+    dwk = torch.empty(shape, dtype=torch.float32, device=x.device)
+    mo = g.shape[0] * g.shape[2] * g.shape[3]
+    taps = ksize * ksize
+    with _T("wgrad3x3" if ksize == 3 else "wgrad1x1", nbytes=2 * (mo * cout + f * h * w * cin) + 4 * taps * cin * cout,
+            flops=2 * mo * cout * taps * cin):
+        rc = _L().conv3x3_wgrad(C.byref(d), ptr(g), ptr(x), ptr(dwk), _stream())
+    _lib.check(rc, "conv3x3_wgrad")
+    return dwk
 
 
 class _Conv3x3(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, stride, stats):
-        wb = weight.detach().to(torch.bfloat16)
-        y, sums = conv3x3_raw(x, wb.permute(0, 2, 3, 1).contiguous(), stride, stats)
-        ctx.stride = stride
+        wb = _wform(weight, "nchw")
+        y, sums = conv3x3_raw(x, _wform(weight, "krsc"), stride, stats)
+        ctx.stride, ctx.weight = stride, weight
         ctx.save_for_backward(x, wb)
         if not stats:
             return y
@@ -309,18 +377,12 @@ class _Conv3x3(torch.autograd.Function):
         need_dx, need_dw = ctx.needs_input_grad[0], ctx.needs_input_grad[1]
         if need_dx and st == 1:
             # stride-1 input gradient = the same convolution with spatially rotated, channel-transposed weights
-            w_rot = wb.flip(2, 3).permute(1, 2, 3, 0).contiguous()          # (Cin, 3, 3, Cout)
-            dx, _ = conv3x3_raw(g, w_rot, 1)
+            dx, _ = conv3x3_raw(g, _wform(ctx.weight, "rot"), 1)          # (Cin, 3, 3, Cout)
             need_dx = False
         # own 3x3 wgrad where it is within ~1.2x of cuDNN (Cin >= 256: layer3/4); the 9-tap re-read of dY makes it
         # 1.5-3.7x slower on the 56x56 / 28x28 layers (tools/wgrad_probe.py), which stay on the library this round
         if need_dw and wgrad_enabled() and (x.shape[1] >= 256 or os.environ.get("MVFB_WGRAD3X3") == "all"):
-            f, cin, h, w = x.shape
-            d = ConvDesc()
-            d.F, d.H, d.W, d.Cin, d.Cout, d.stride, d.ksize = f, h, w, cin, wb.shape[0], st, 3
-            dwk = torch.empty((wb.shape[0], 3, 3, cin), dtype=torch.float32, device=x.device)
-            _lib.check(_L().conv3x3_wgrad(C.byref(d), ptr(g), ptr(x), ptr(dwk), _stream()), "conv3x3_wgrad")
-            dw = dwk.permute(0, 3, 1, 2)                                  # (Cout, Cin, 3, 3) view of the KRSC buffer
+            dw = conv3x3_wgrad_raw(g, x, wb.shape[0], st, 3).permute(0, 3, 1, 2)   # (Cout, Cin, 3, 3) view of KRSC
             need_dw = False
         if need_dx or need_dw:
             wcl = wb.contiguous(memory_format=torch.channels_last)
@@ -340,10 +402,9 @@ class _Conv1x1Strided(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, weight, stride, stats):
-        cout, cin = weight.shape[0], weight.shape[1]
-        wb = weight.detach().reshape(cout, cin).to(torch.bfloat16)
+        wb = _wform(weight, "rows")
         y, sums = conv3x3_raw(x, wb, stride, stats)
-        ctx.stride = stride
+        ctx.stride, ctx.weight = stride, weight
         ctx.save_for_backward(x, wb)
         if not stats:
             return y
@@ -358,16 +419,12 @@ class _Conv1x1Strided(torch.autograd.Function):
         g = g.contiguous(memory_format=torch.channels_last)
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dxc, _, _ = gemm_tn(_rows(g), wb.t().contiguous())                       # (F*Ho*Wo, Cin)
+            dxc, _, _ = gemm_tn(_rows(g), _wform(ctx.weight, "rowsT"))               # (F*Ho*Wo, Cin)
             dx = torch.zeros((f, h, w, cin), dtype=torch.bfloat16, device=x.device)
             dx[:, ::st, ::st, :] = dxc.view(f, g.shape[2], g.shape[3], cin)
             dx = dx.permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
-            d = ConvDesc()
-            d.F, d.H, d.W, d.Cin, d.Cout, d.stride, d.ksize = f, h, w, cin, wb.shape[0], st, 1
-            dwk = torch.empty((wb.shape[0], cin), dtype=torch.float32, device=x.device)
-            _lib.check(_L().conv3x3_wgrad(C.byref(d), ptr(g), ptr(x), ptr(dwk), _stream()), "conv3x3_wgrad")
-            dw = dwk.view(wb.shape[0], cin, 1, 1)
+            dw = conv3x3_wgrad_raw(g, x, wb.shape[0], st, 1).view(wb.shape[0], cin, 1, 1)
         return dx, dw, None, None
 
 
@@ -410,7 +467,8 @@ class _StemConv(torch.autograd.Function):
         ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
         xb = x.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)   # (F, H, W, 3) in memory
         a = torch.empty((f * ho * wo, STEM_KP), dtype=torch.bfloat16, device=x.device)
-        _lib.check(L.stem_im2col(ptr(xb), ptr(a), f, h, w, _stream()), "stem_im2col")
+        with _T("stem_im2col", nbytes=2 * (xb.numel() + a.numel())):
+            _lib.check(L.stem_im2col(ptr(xb), ptr(a), f, h, w, _stream()), "stem_im2col")
         wm = torch.zeros((64, STEM_KP), dtype=torch.bfloat16, device=x.device)
         wm[:, :STEM_K] = weight.detach().permute(0, 2, 3, 1).reshape(64, STEM_K)           # K order (kh, kw, c)
         out, colsum, _ = gemm_tn(a, wm, stats=stats)
@@ -457,7 +515,8 @@ class _MaxPool3x3s2(torch.autograd.Function):
         ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
         y = torch.empty((f, ho, wo, c), dtype=torch.bfloat16, device=x.device)
         idx = torch.empty((f, ho, wo, c), dtype=torch.uint8, device=x.device)
-        _lib.check(L.maxpool3x3s2_fwd(ptr(x), ptr(y), ptr(idx), f, h, w, c, _stream()), "maxpool3x3s2_fwd")
+        with _T("maxpool", nbytes=2 * x.numel() + 3 * y.numel()):
+            _lib.check(L.maxpool3x3s2_fwd(ptr(x), ptr(y), ptr(idx), f, h, w, c, _stream()), "maxpool3x3s2_fwd")
         ctx.save_for_backward(idx)
         ctx.shape = (f, c, h, w)
         return y.permute(0, 3, 1, 2)
@@ -469,7 +528,8 @@ class _MaxPool3x3s2(torch.autograd.Function):
         f, c, h, w = ctx.shape
         g = g.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
         dx = torch.empty((f, h, w, c), dtype=torch.bfloat16, device=g.device)
-        _lib.check(L.maxpool3x3s2_bwd(ptr(g), ptr(idx), ptr(dx), f, h, w, c, _stream()), "maxpool3x3s2_bwd")
+        with _T("maxpool", nbytes=3 * g.numel() + 2 * dx.numel()):
+            _lib.check(L.maxpool3x3s2_bwd(ptr(g), ptr(idx), ptr(dx), f, h, w, c, _stream()), "maxpool3x3s2_bwd")
         return dx.permute(0, 3, 1, 2)
 
 
@@ -503,7 +563,8 @@ class _BNAct(torch.autograd.Function):
         save = torch.empty((2, c), dtype=torch.float32, device=dev)
         if training and sums is None:
             sums = torch.empty((2, c), dtype=torch.float32, device=dev)
-            _lib.check(L.bn_stats(C.byref(d), ptr(xr), xr.stride(0), ptr(sums), _stream()), "bn_stats")
+            with _T("bn_fwd", nbytes=2 * xr.numel()):
+                _lib.check(L.bn_stats(C.byref(d), ptr(xr), xr.stride(0), ptr(sums), _stream()), "bn_stats")
         rr = _rows(residual) if residual is not None else None
         g32 = gamma if gamma.dtype == torch.float32 else gamma.float()
         b32 = beta if beta.dtype == torch.float32 else beta.float()
@@ -511,9 +572,11 @@ class _BNAct(torch.autograd.Function):
         mask = None
         if relu and any(ctx.needs_input_grad[:3]):
             mask = torch.empty(xr.shape[0] * (c // 8), dtype=torch.uint8, device=dev)
-        rc = L.bn_apply(C.byref(d), ptr(xr), xr.stride(0), ptr(rr), rr.stride(0) if rr is not None else 0, ptr(y), c,
-                        ptr(sums), ptr(g32), ptr(b32), ptr(running_mean), ptr(running_var), ptr(save[0]), ptr(save[1]),
-                        ptr(mask), _stream())
+        ne = xr.numel()
+        with _T("bn_fwd", nbytes=2 * ne * (3 if rr is not None else 2) + (ne // 8 if mask is not None else 0)):
+            rc = L.bn_apply(C.byref(d), ptr(xr), xr.stride(0), ptr(rr), rr.stride(0) if rr is not None else 0, ptr(y), c,
+                            ptr(sums), ptr(g32), ptr(b32), ptr(running_mean), ptr(running_var), ptr(save[0]),
+                            ptr(save[1]), ptr(mask), _stream())
         _lib.check(rc, "bn_apply")
         yv = y.permute(0, 3, 1, 2)
         ctx.relu, ctx.training, ctx.has_res, ctx.eps = relu, training, residual is not None, eps
@@ -535,9 +598,13 @@ class _BNAct(torch.autograd.Function):
         dres = torch.empty((f, h, w, c), dtype=torch.bfloat16, device=dev) if ctx.has_res else None
         grads = torch.empty((2, c), dtype=torch.float32, device=dev)
         scratch = torch.empty((2, c), dtype=torch.float32, device=dev)
-        rc = L.bn_bwd(C.byref(d), ptr(gr), gr.stride(0), ptr(yr), yr.stride(0) if yr is not None else 0, ptr(xr),
-                      xr.stride(0), ptr(gamma), ptr(save[0]), ptr(save[1]), ptr(dx), c, ptr(dres), c, ptr(grads[0]),
-                      ptr(grads[1]), ptr(scratch), ptr(mask), _stream())
+        ne = xr.numel()
+        # reduce: reads g, x (, mask | y);  apply: reads g, x (, mask | y), writes dx (, d residual)
+        rd = 2 * ne * 2 + (ne // 8 if mask is not None else (2 * ne if yr is not None else 0))
+        with _T("bn_bwd", nbytes=2 * rd + 2 * ne * (2 if dres is not None else 1)):
+            rc = L.bn_bwd(C.byref(d), ptr(gr), gr.stride(0), ptr(yr), yr.stride(0) if yr is not None else 0, ptr(xr),
+                          xr.stride(0), ptr(gamma), ptr(save[0]), ptr(save[1]), ptr(dx), c, ptr(dres), c, ptr(grads[0]),
+                          ptr(grads[1]), ptr(scratch), ptr(mask), _stream())
         _lib.check(rc, "bn_bwd")
         dres_v = dres.permute(0, 3, 1, 2) if dres is not None else None
         return dx.permute(0, 3, 1, 2), grads[0], grads[1], None, None, dres_v, None, None, None, None, None

@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY.  Run in the build container (the GPU box has no /root/reference):
 
-    python oracle/make_golden.py            # writes tests/golden/{mvf_cases,bottleneck_cases,model_r50}.npz
+    python oracle/make_golden.py            # writes tests/golden/{mvf_cases,bottleneck_cases,model_r50,model_r50_224}.npz
 
 The reference is imported from /root/reference with `oracle/mmcv_stub` standing in for mmcv 0.4.3
 (import-time names and init helpers only; no arithmetic).  Inputs are generator-seeded torch tensors;
@@ -198,6 +198,39 @@ def model_case(depth=50, t=4, b=2, px=64, seed=0):
     return rec
 
 
+FULL_GRADS_224 = ("backbone.conv1.weight", "backbone.layer1.0.conv1.weight", "backbone.layer2.0.conv2.weight",
+                  "backbone.layer3.2.conv1.net.weight", "cls_head.new_fc.bias")
+
+
+def model_case_224(depth=50, t=8, b=2, px=224, seed=3):
+    """The bench configuration's geometry (T = 8, 224 px: 56/28/14/7 stage resolutions, MVF on 14x14 and 7x7 slabs) at
+    B = 2 clips, fp32, train mode: loss, every parameter's gradient norm, the full gradient of every 1-D parameter
+    (BatchNorm affine, bias), of every MVF tap tensor and of a few convolutions.  The input is NOT stored (9.6 MB):
+    it is regenerated from the seed with the CPU generator, its checksum is."""
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = build_recognizer(model_cfg(depth, t, 0.0), None, dict(average_clips="prob"))
+    sd = synth_state_dict(seed, depth=depth, n_segment=t)
+    m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(seed + 1)
+    img = torch.randn((b, t, 3, px, px), generator=g)
+    label = torch.randint(0, 400, (b, 1), generator=g)
+    rec = {"meta": np.array([depth, t, b, px, seed]), "label": label.numpy(),
+           "img_checksum": np.array([img.double().sum().item(), img.double().abs().sum().item()])}
+    m.train()
+    loss = m(img, label)["loss_cls"]
+    loss.backward()
+    rec["train_loss"] = np.array(loss.item())
+    names, norms = [], []
+    for k, p in m.named_parameters():
+        names.append(k)
+        norms.append(p.grad.double().norm().item())
+        if p.dim() == 1 or "shift_conv" in k or "h_conv" in k or "w_conv" in k or k in FULL_GRADS_224:
+            rec["grad." + k] = p.grad.numpy().copy()
+    rec["grad_names"] = np.array(names)
+    rec["grad_norms"] = np.array(norms)
+    return rec
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -210,6 +243,7 @@ def main():
         recs.update(bottleneck_case(*c, seed=200 + i))
     np.savez_compressed(os.path.join(OUT, "bottleneck_cases.npz"), **recs)
     np.savez_compressed(os.path.join(OUT, "model_r50.npz"), **model_case(50, 4, 2, 64, 0))
+    np.savez_compressed(os.path.join(OUT, "model_r50_224.npz"), **model_case_224())
     # structural known-answers (config docstrings r50_dense.py:1-5 / r101_dense.py:1-5)
     counts = {}
     for depth in (50, 101):

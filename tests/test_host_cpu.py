@@ -219,3 +219,55 @@ def test_two_rank_gradient_allreduce_matches_single_process():
     for p, q in zip(net.parameters(), a["g"]):
         assert torch.allclose(p.grad, q, atol=1e-6)
     assert a["numel"] == sum(p.numel() for p in net.parameters())
+
+
+def _mvf_desc(N, T, C, Cs, H, dtype=1, layout=1, training=1):
+    from mvfnet_b200 import _lib
+    d = _lib.MvfDesc()
+    d.N, d.T, d.C, d.Cs, d.H, d.W = N, T, C, Cs, H, H
+    d.dtype, d.layout, d.mode, d.use_hs, d.training = dtype, layout, 2, 1, training
+    d.eps, d.momentum = 1e-5, 0.1
+    return d
+
+
+def test_kernel_tier_plan_is_pinned_without_gpu():
+    """Which kernel tier serves which shape is part of the contract (host-only query mvf_b200_plan): every R50 / R101
+    slab shape at 224 and 256 px with the configs' frame counts runs on the sweep kernels, forward and backward; other
+    frame counts step down to the stream tier, fp32 / NCHW / ragged shapes to the generic kernels.  The GPU tests assert
+    that mvf_b200_last_kernel() agrees with this plan after every call."""
+    from mvfnet_b200 import _lib
+    model_shapes = [(512, 28, 64), (1024, 14, 128), (2048, 7, 256), (512, 32, 64), (1024, 16, 128), (2048, 8, 256)]
+    for C, H, Cs in model_shapes:
+        for T in (4, 8, 16):
+            for N in (1, 12, 160):
+                for training in (0, 1):
+                    d = _mvf_desc(N, T, C, Cs, H, training=training)
+                    assert _lib.plan(d) == "sweep", (C, H, T, N, training)
+                    assert _lib.plan(d, True) in EXPECTED_BWD_TIER[(C, H)], (C, H, T, N, training, _lib.plan(d, True))
+        assert _lib.plan(_mvf_desc(12, 5, C, Cs, H)) == "stream"
+        assert _lib.plan(_mvf_desc(12, 8, C, Cs, H, dtype=0)) == "generic"          # fp32 parity path
+        assert _lib.plan(_mvf_desc(12, 8, C, Cs, H, layout=0)) == "generic"         # NCHW
+    assert _lib.plan(_mvf_desc(2, 8, 24, 3, 5)) == "generic"                        # ragged channel count
+    bad = _mvf_desc(2, 8, 24, 30, 5)                                                # Cs > C
+    assert _lib.plan(bad) == ""
+
+
+# backward tier per (C, H); updated together with the kernels (csrc/api.cu::mvf_bwd)
+EXPECTED_BWD_TIER = {(512, 28): ("ring",), (1024, 14): ("stream",), (2048, 7): ("stream",), (512, 32): ("generic",),
+                     (1024, 16): ("ring",), (2048, 8): ("stream",)}
+
+
+def test_force_option_and_last_kernel_without_gpu():
+    from mvfnet_b200 import _lib
+    L = _lib.lib()
+    assert _lib.last_kernel() in ("", "sweep", "stream", "ring", "generic")
+    d = _mvf_desc(12, 8, 1024, 128, 14)
+    try:
+        for tier in ("stream", "ring", "generic"):
+            _lib.set_option(_lib.OPT_FORCE_FWD, _lib.KERNELS[tier])
+            assert _lib.plan(d) == tier
+        _lib.set_option(_lib.OPT_FORCE_FWD, _lib.KERNELS["sweep"])
+        assert _lib.plan(_mvf_desc(12, 5, 1024, 128, 14)) == ""                     # a forced tier never falls through
+    finally:
+        _lib.set_option(_lib.OPT_FORCE_FWD, 0)
+    assert L.mvf_b200_set_option(99, 1) != 0 and b"unknown option" in L.mvf_b200_last_error()

@@ -93,6 +93,85 @@ def test_whole_model_golden_fp32():
     assert rel_err(rm, z["rm_after.layer4.2.conv1.bn"]) < 1e-3
 
 
+def _golden_224():
+    z = np.load(GOLDEN + "/model_r50_224.npz")
+    depth, t, b, px, seed = [int(v) for v in z["meta"]]
+    g = torch.Generator().manual_seed(seed + 1)
+    img = torch.randn((b, t, 3, px, px), generator=g)
+    label = torch.randint(0, 400, (b, 1), generator=g)
+    chk = np.array([img.double().sum().item(), img.double().abs().sum().item()])
+    np.testing.assert_allclose(chk, z["img_checksum"], rtol=1e-12, err_msg="the seeded input is not the golden run's")
+    assert np.array_equal(label.numpy(), z["label"])
+    return z, depth, t, seed, img, label
+
+
+def _rel_l2(a, b):
+    a, b = np.asarray(a, np.float64).ravel(), np.asarray(b, np.float64).ravel()
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+def test_whole_model_224_fp32_gradients_vs_reference():
+    """R50 8x8 at 224 px (the bench geometry), B = 2, fp32: loss and EVERY stored gradient of the unmodified reference
+    (oracle/make_golden.py::model_case_224) within 1e-3 relative L2; every parameter's gradient norm within 1e-3."""
+    from mvfnet_b200 import build_recognizer
+    z, depth, t, seed, img, label = _golden_224()
+    m = build_recognizer(model_cfg(depth, t, 0.0), None, None)
+    m.load_state_dict(synth_state_dict(seed, depth=depth, n_segment=t))
+    m = m.cuda().train()
+    loss = m(img.cuda(), label.cuda())["loss_cls"]
+    loss.backward()
+    assert abs(loss.item() - float(z["train_loss"])) < 1e-4 * abs(float(z["train_loss"]))
+    params = dict(m.named_parameters())
+    norms = dict(zip([str(k) for k in z["grad_names"]], z["grad_norms"]))
+    for k, p in params.items():
+        assert abs(p.grad.double().norm().item() - norms[k]) <= 1e-3 * norms[k] + 1e-9, k
+    for k in z.files:
+        if k.startswith("grad."):
+            assert _rel_l2(params[k[5:]].grad.cpu().numpy(), z[k]) < 1e-3, k
+
+
+def test_whole_model_224_bf16_fused_gradients_vs_reference():
+    """The SAME golden through the production configuration (bf16 autocast, channels_last: every convolution, BatchNorm,
+    MVF module, the stem and the max-pool on this library's kernels).  bf16 storage of ~160 activations / gradients in
+    sequence: each parameter's gradient must agree with the fp32 reference within 5e-2 relative L2 (1e-2 per rounding
+    compounding over the depth of the network; measured values are written to gpurun_out/ for the record), its norm
+    within 5e-2, the loss within 1e-2."""
+    import json
+    import os
+    from mvfnet_b200 import build_recognizer, _lib
+    from mvfnet_b200.utils import to_channels_last
+    z, depth, t, seed, img, label = _golden_224()
+    m = build_recognizer(model_cfg(depth, t, 0.0), None, None)
+    m.load_state_dict(synth_state_dict(seed, depth=depth, n_segment=t))
+    m = to_channels_last(m.cuda()).train()
+    before = _lib.launch_count()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = m(img.cuda(), label.cuda())["loss_cls"]
+    loss.backward()
+    torch.cuda.synchronize()
+    assert _lib.launch_count() - before > 300, "the fused kernels were not used"
+    params = dict(m.named_parameters())
+    norms = dict(zip([str(k) for k in z["grad_names"]], z["grad_norms"]))
+    rec = {"loss": loss.item(), "ref_loss": float(z["train_loss"]), "rel_l2": {}, "norm_ratio": {}}
+    for k, p in params.items():
+        rec["norm_ratio"][k] = p.grad.double().norm().item() / max(norms[k], 1e-30)
+    for k in z.files:
+        if k.startswith("grad."):
+            rec["rel_l2"][k[5:]] = _rel_l2(params[k[5:]].grad.float().cpu().numpy(), z[k])
+    out = os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "bf16_model_grad_parity.json"), "w") as f:
+            json.dump(rec, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+    assert abs(rec["loss"] - rec["ref_loss"]) < 1e-2 * abs(rec["ref_loss"])
+    worst = sorted(rec["rel_l2"].items(), key=lambda kv: -kv[1])[:5]
+    assert worst[0][1] < 5e-2, worst
+    bad = {k: v for k, v in rec["norm_ratio"].items() if abs(v - 1.0) > 5e-2}
+    assert not bad, sorted(bad.items(), key=lambda kv: -abs(kv[1] - 1))[:5]
+
+
 def test_whole_model_bf16_channels_last_runs():
     """The bench configuration (bf16 autocast, channels_last): loss close to the fp32 golden loss."""
     from mvfnet_b200 import build_recognizer

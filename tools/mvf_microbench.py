@@ -86,7 +86,7 @@ def main():
                             flush.zero_()
                         bwd()
                     torch.cuda.synchronize()
-                    rec = [s.elapsed_time(e) * 1e3 for k, b, s, e in mm.timing_end() if k == "mvf_bwd"][3:]
+                    rec = [s.elapsed_time(e) * 1e3 for k, b, s, e, _ in mm.timing_end() if k == "mvf_bwd"][3:]
                     rec.sort()
                     med = rec[len(rec) // 2]
                     row = dict(kernel="mvf_bwd", T=T, C=C, H=H, Cs=Cs, clips=B, training=training, us_median=med,

@@ -1,9 +1,8 @@
 #!/usr/bin/env python
-"""In-kernel timeline of the MVF forward kernel (MVFB_SWEEP_DEBUG=1 makes every CTA of mvf_sweep_kernel write
+"""In-kernel timeline of the MVF forward kernel (mvf_b200_set_option(MVFB_OPT_SWEEP_DEBUG, 1) makes every CTA of mvf_sweep_kernel write
 %globaltimer stamps: start, prologue done, first frame landed, [train: statistics sweep done, grid barrier passed],
 last frame stored) next to the CUDA-event duration of the same launch and of an empty launch."""
 import os, sys, ctypes as C
-os.environ["MVFB_SWEEP_DEBUG"] = "1"
 import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -11,6 +10,7 @@ from mvfnet_b200 import MVF, _lib
 from mvfnet_b200.mvf import _make_desc, ptr, _stream
 
 lib = _lib.lib()
+_lib.set_option(_lib.OPT_SWEEP_DEBUG, 1)
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 tiny = torch.zeros(32, device="cuda")
 for it in range(6):
