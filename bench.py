@@ -276,7 +276,8 @@ def run_ours(args):
     import torch.distributed as dist
     from mvfnet_b200 import build_recognizer, _lib
     from mvfnet_b200 import mvf as mvf_mod
-    from mvfnet_b200.dist import FlatGrads, init_dist
+    from mvfnet_b200.dist import init_dist
+    from mvfnet_b200.tail import FlatSGD, preprocess_frames
     from mvfnet_b200.utils import to_channels_last
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -295,13 +296,16 @@ def run_ours(args):
     if world > 1:                                                  # MMDistributedDataParallel: broadcast once
         for t in model.state_dict().values():
             dist.broadcast(t, 0)
-    flat = FlatGrads(model.parameters())
-    opt = torch.optim.SGD(model.parameters(), lr=0.015, momentum=0.9, weight_decay=1e-4, nesterov=True)
-    params = [p for p in model.parameters() if p.requires_grad]
+    # optimizer + grad_clip of the recipe (r50_dense.py:152-154) on flat buffers: one all-reduce, one fused update
+    opt = FlatSGD(model.parameters(), lr=0.015, momentum=0.9, weight_decay=1e-4, nesterov=True, max_norm=40)
+    u8 = args.input == "u8"
 
     def make_batches(b, seed):
         g = torch.Generator().manual_seed(seed + rank)             # each rank owns different clips
-        himg = [torch.randn((b, T_FRAMES, 3, PX, PX), generator=g).pin_memory() for _ in range(2)]
+        if u8:      # decoded frames as the pipeline's FrameSelector delivers them: uint8 HWC (B, T, H, W, 3)
+            himg = [torch.randint(0, 256, (b, T_FRAMES, PX, PX, 3), generator=g, dtype=torch.uint8).pin_memory() for _ in range(2)]
+        else:       # the reference's wire format: float32 (B, T, 3, H, W), already normalised on the CPU
+            himg = [torch.randn((b, T_FRAMES, 3, PX, PX), generator=g).pin_memory() for _ in range(2)]
         hlbl = [torch.randint(0, 400, (b, 1), generator=g).pin_memory() for _ in range(2)]
         return himg, hlbl
 
@@ -310,15 +314,15 @@ def run_ours(args):
     dev_lbl = [h.to(dev) for h in host_lbl]
 
     def train_step(img, label):
-        flat.zero_()
+        """DistOptimizerHook.after_train_iter's order (core/dist_utils.py:59-67): zero_grad, forward, backward, ONE
+        all-reduce, clip, SGD step -- the last three inside FlatSGD.step()."""
+        opt.zero_grad()
+        if u8:
+            img = preprocess_frames(img)                             # Normalize + FormatShape on the GPU
         with torch.autocast("cuda", dtype=torch.bfloat16):
             loss = model(img, label)["loss_cls"]
         loss.backward()
-        if world > 1:
-            flat.gather()
-            flat.allreduce_()
-        torch.nn.utils.clip_grad_norm_(params, max_norm=40, norm_type=2)
-        opt.step()
+        opt.step(world)
         return loss
 
     def barrier():
@@ -404,7 +408,7 @@ def run_ours(args):
     barrier()
     ms_e2e = max_over_ranks(t0.elapsed_time(t1))
     e2e_value = world * B * args.steps / (ms_e2e / 1e3)
-    h2d = host_img[0].numel() * 4 + host_lbl[0].numel() * 8
+    h2d = host_img[0].numel() * host_img[0].element_size() + host_lbl[0].numel() * 8
     peak_gb = round(torch.cuda.max_memory_allocated(dev) / 2**30, 1)
     del slots_img, slots_lbl, dev_img, dev_lbl, host_img, host_lbl
 
@@ -425,7 +429,7 @@ def run_ours(args):
     bar = None
     if not args.no_gpu_bar:
         import gc
-        del model, opt, flat, params
+        del model, opt
         gc.collect()
         torch.cuda.empty_cache()
         bar = gpu_bar(dev, world, rank, [12, 64] + ([B] if B not in (12, 64) else []))
@@ -490,6 +494,8 @@ def run_ours(args):
                                    "clip+SGD step, B=%d clips per GPU%s" % (DEPTH, T_FRAMES, 64 // T_FRAMES, T_FRAMES, B,
                                    " (BASELINE.json configs[1])" if (DEPTH, T_FRAMES) == (50, 8) else ""),
                        "clips_per_gpu": B, "frames_per_gpu": B * T_FRAMES, "parallelism": "dp%d" % world,
+                       "input": ("uint8 (B,T,H,W,3) decoded frames, Normalize + FormatShape on the GPU (preprocess_u8)" if u8
+                                 else "float32 (B,T,3,H,W) normalised on the host (the reference's wire format)"),
                        "l2": "no flush: one step streams >10 GB of activations, far above the 126 MB L2",
                        "peak_hbm_gb": peak_gb},
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
@@ -520,6 +526,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--depth", type=int, default=DEPTH, help="ResNet depth (50: BASELINE configs[1]; 101: configs[3])")
     ap.add_argument("--frames", type=int, default=T_FRAMES, help="frames per clip T (8: configs[1]; 16: configs[2])")
+    ap.add_argument("--input", default="u8", choices=["u8", "f32"],
+                    help="u8: decoded uint8 frames, normalised on the GPU; f32: the reference's float32 wire format")
     ap.add_argument("--sweep", default="12,64", help="extra clips-per-GPU sizes our arm is also timed at (resident inputs)")
     ap.add_argument("--no-gpu-bar", action="store_true", help="skip the reference-on-PyTorch/cuDNN arm (gpu_bar)")
     ap.add_argument("--kernels-only", action="store_true",

@@ -41,7 +41,8 @@ int mvf_b200_version(void);
 const char* mvf_b200_last_error(void);
 /* Number of kernels launched by this library in this process so far (bench.py `gpu_launches`). */
 unsigned long long mvf_b200_launch_count(void);
-/* Kernel tier that served the last successful mvf_fwd / mvf_bwd call of the calling thread: "sweep" (persistent
+/* Kernel tier that served the last successful mvf_fwd / mvf_bwd call of this PROCESS (any thread: autograd runs the
+ * backward on its own engine thread): "sweep" (persistent
  * frame-stream kernels on the bf16-operand FMA, mvf_sweep.cu / mvf_sweep_bwd.cu), "stream" (mvf_stream*.cu), "ring"
  * (mvf_fast.cu) or "generic" (any layout / dtype, mvf_generic.cu); "" before the first call.  The parity tests assert
  * it, so a silent fall-through to a slower tier fails them. */
@@ -219,8 +220,9 @@ int bn_bwd(const mvfb_bn_desc* d, const void* g, long long ldg, const void* y, l
  * maxpool = nn.MaxPool2d(3, 2, 1) of ResNet.forward (backbones/resnet.py:424-431, 481-484).
  *
  *   stem_im2col      : x (F, H, W, 3) bf16 NHWC -> a (F*Ho*Wo, 192) bf16 row-major, Ho = (H-1)/2+1: the 7x7x3
- *                      patch of every output pixel, K ordered (kh, kw, c), zero padded from 147 to 192 columns.
- *                      conv1x1_gemm(a, W (64,192)) is then the convolution (BatchNorm sums in its epilogue) and
+ *                      patch of every output pixel, column k = kh*24 + kw*3 + c (each kernel row = 21 values + 3
+ *                      zeros: three aligned 16-byte chunks; columns 168..191 zero).  conv1x1_gemm(a, W (64,192) in the
+ *                      same column order) is then the convolution (BatchNorm sums in its epilogue) and
  *                      conv1x1_wgrad(dY, a) its weight gradient.
  *   maxpool3x3s2_fwd : x (F, H, W, C) bf16 NHWC -> y (F, Ho, Wo, C) and idx (F, Ho, Wo, C) bytes = position of the
  *                      maximum inside the 3x3 window (kh*3 + kw; the first maximum in scan order, NaN wins: the
@@ -231,6 +233,57 @@ int bn_bwd(const mvfb_bn_desc* d, const void* g, long long ldg, const void* y, l
 int stem_im2col(const void* x, void* a, long long F, int H, int W, mvfb_stream_t stream);
 int maxpool3x3s2_fwd(const void* x, void* y, void* idx, long long F, int H, int W, int C, mvfb_stream_t stream);
 int maxpool3x3s2_bwd(const void* g, const void* idx, void* dx, long long F, int H, int W, int C, mvfb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Input pre-processing on the GPU  --  replaces Normalize + FormatShape + ToTensor of the data pipeline
+ * (codes/datasets/pipelines/augmentations.py:343-396, formating.py:134-185; configs r50_dense.py:70-75) for frames that
+ * arrive as decoded uint8 images: y[p, c] = (float(x[p, to_rgb ? 2 - c : c]) - mean[c]) / std[c], written as bf16 in
+ * the NHWC frame layout the stem reads.  x: (pixels, 3) uint8 HWC frames back to back (pixels % 4 == 0);
+ * mean / std: HOST pointers to 3 floats, indexed by the output channel as mmcv.imnormalize applies them.
+ * ---------------------------------------------------------------------------------------------- */
+int preprocess_u8(const void* x, void* y, long long pixels, const float* mean, const float* std_, int to_rgb,
+                  mvfb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Classification head and loss  --  replaces TSNClsHead.forward + BaseHead.loss (codes/models/heads/tsn_clshead.py:71-98,
+ * heads/base.py:40-45, segmental_consensuses/simple_consensus.py:41-61) around the 2048 -> num_classes projection,
+ * which runs on conv1x1_gemm / conv1x1_wgrad with the class axis zero-padded to a multiple of 64 (ldl columns):
+ *
+ *   head_pool_fwd : feat[f, c] = dropout_p( mean over the HW pixels of x[f, :, c] )   x (F, HW, C) bf16 NHWC -> (F, C) bf16
+ *                   (the keep decision of element (f, c) is a counter-based hash of (seed, f*C + c): the backward
+ *                   recomputes it, no mask is stored; p = 0 disables dropout)
+ *   head_ce_fwd   : s[b, c] = bias[c] + mean_t logits[b*T + t, c]  (SimpleConsensus 'avg' over the T segments);
+ *                   loss = mean_b ( logsumexp(s[b]) - s[b, label[b]] );  ds = d loss / d s  (B, NC) fp32;
+ *                   dbias[c] = sum_b ds[b, c];  score (optional) receives s.  loss / dbias are zeroed by the call.
+ *   head_ce_bwd   : dlogits[b*T + t, c] = gout * ds[b, c] / T  (bf16, (B*T, ldl), padding columns zero);
+ *                   gout = device pointer to d L / d loss (NULL = 1).
+ *   head_pool_bwd : dx[f, q, c] = dfeat[f, c] * keep(f, c) / ((1 - p) * HW)  for every pixel q.
+ * ---------------------------------------------------------------------------------------------- */
+int head_pool_fwd(const void* x, void* feat, long long F, int HW, int C, float p, unsigned long long seed,
+                  mvfb_stream_t stream);
+int head_pool_bwd(const void* dfeat, void* dx, long long F, int HW, int C, float p, unsigned long long seed,
+                  mvfb_stream_t stream);
+int head_ce_fwd(const void* logits, long long ldl, const float* bias, const long long* labels, int B, int T, int NC,
+                float* score, float* ds, float* dbias, float* loss, mvfb_stream_t stream);
+int head_ce_bwd(const float* ds, const float* gout, void* dlogits, long long ldl, int B, int T, int NC,
+                mvfb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Optimizer tail  --  replaces what DistOptimizerHook.after_train_iter does after the all-reduce
+ * (codes/core/dist_utils.py:29-32, 59-67 with optimizer / grad_clip of r50_dense.py:152-154): divide by the world size,
+ * clip the global gradient norm, torch.optim.SGD(momentum, weight_decay, nesterov) -- over FLAT fp32 buffers:
+ *
+ *   flat_sqnorm       : out (device double, zeroed by the call) = sum_i g[i]^2
+ *   sgd_nesterov_step : c = grad_scale * min(1, max_norm / (sqrt(sqnorm) * grad_scale + 1e-6))   (max_norm <= 0: c = grad_scale)
+ *                       g' = c g + weight_decay p;  m = momentum m + g';  p -= lr (nesterov ? g' + momentum m : m)
+ *                       p_bf16 (optional) receives the updated parameters rounded to bf16 -- the operands the next
+ *                       forward's GEMMs read; norm_out (optional, device float) the total norm sqrt(sqnorm) * grad_scale.
+ *                       A zero-initialised m reproduces torch's first step (buf = grad).
+ * ---------------------------------------------------------------------------------------------- */
+int flat_sqnorm(const float* g, long long n, double* out, mvfb_stream_t stream);
+int sgd_nesterov_step(float* p, float* mom, const float* g, void* p_bf16, long long n, const double* sqnorm,
+                      float* norm_out, float grad_scale, float max_norm, float lr, float momentum, float weight_decay,
+                      int nesterov, mvfb_stream_t stream);
 
 #ifdef __cplusplus
 }

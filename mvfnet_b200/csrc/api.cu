@@ -37,8 +37,9 @@ int num_sms() {
   return n;
 }
 
-static thread_local const char* g_last_kernel = "";
-void note_kernel(const char* name) { g_last_kernel = name; }
+// process-wide, not thread-local: autograd runs the backward on its own engine thread, the test that asks is on another
+static std::atomic<const char*> g_last_kernel{""};
+void note_kernel(const char* name) { g_last_kernel.store(name, std::memory_order_relaxed); }
 
 static std::atomic<int> g_options[OPT_COUNT];
 int option(int key) { return key >= 0 && key < OPT_COUNT ? g_options[key].load(std::memory_order_relaxed) : 0; }
@@ -121,7 +122,7 @@ extern "C" {
 int mvf_b200_version(void) { return MVFB_VERSION; }
 const char* mvf_b200_last_error(void) { return g_err; }
 unsigned long long mvf_b200_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
-const char* mvf_b200_last_kernel(void) { return g_last_kernel; }
+const char* mvf_b200_last_kernel(void) { return g_last_kernel.load(std::memory_order_relaxed); }
 const char* mvf_b200_plan(const mvfb_mvf_desc* d, int backward) {
   if (check_mvf_desc(d)) return "";
   const int force = option(backward ? OPT_FORCE_BWD : OPT_FORCE_FWD);

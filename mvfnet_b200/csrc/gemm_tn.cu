@@ -15,9 +15,13 @@
 //   warp 1   MMA issuer     one elected lane issues tcgen05.mma.cta_group::1.kind::f16 (M=128, N=BN, K=16),
 //                           fp32 accumulators in TMEM, double-buffered (2 x BN columns) so the epilogue of tile i
 //                           overlaps the main loop of tile i+1; tcgen05.commit releases smem slots / signals TMEM
-//   warps 2-5 epilogue      tcgen05.ld 32x32b -> bf16 -> 128B-swizzled staging tile in smem -> per-column
+//   warps 2-9 epilogue      tcgen05.ld 32x32b -> bf16 -> 128B-swizzled staging tile in smem -> per-column
 //                           (sum, sum of squares) of the ROUNDED outputs for the following train-mode BatchNorm
-//                           (one fp32 atomicAdd per column per tile) -> TMA store (clips the M tail)
+//                           (fp32 atomicAdd per column and row half per tile) -> TMA store (clips the M tail).
+//                           A warp reads the TMEM lanes of its quarter (warp % 4); the two warps of a quarter split
+//                           the tile's columns.  Eight warps because the memory-bound layers (K = 64 .. 256) are paced
+//                           by the epilogue: a 128 x 256 tile is ~500 instructions per thread (TMEM -> bf16 -> smem,
+//                           2 FMAs per element for the statistics) against ~3400 clocks of HBM time per tile.
 #include <cuda_bf16.h>
 
 #include "common.cuh"
@@ -30,8 +34,9 @@ namespace {
 
 constexpr int BM = 128;            // tile rows (UMMA M)
 constexpr int BK = 64;             // K per stage: 64 bf16 = 128 B = one swizzle atom
-constexpr int kThreads = 192;      // 6 warps
-constexpr int kEpiThreads = 128;
+constexpr int kEpiWarps = 8;       // two epilogue warps per TMEM lane quarter: each takes half of the tile's columns
+constexpr int kEpiThreads = 32 * kEpiWarps;
+constexpr int kThreads = 64 + kEpiThreads;   // + TMA producer warp + MMA issuer warp
 
 struct GemmArgs {
   long long M;
@@ -171,10 +176,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     }
   } else {
-    // ===================== epilogue (warps 2..5) =====================
-    const int et = threadIdx.x - 64;                           // 0..127
+    // ===================== epilogue (warps 2..9) =====================
+    const int et = threadIdx.x - 64;                           // 0..255
     const int lane_grp = warp & 3;                             // TMEM lanes [32*lane_grp, +32) belong to this warp
+    const int half = (warp - 2) >> 2;                          // which half of the tile's columns this warp converts
     const int row = lane_grp * 32 + lane;                      // output row within the tile
+    constexpr int kHalfN = BN / 2;
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
@@ -183,7 +190,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // optional addend (out = A B^T + res): this thread's row of it, 32 columns (64 contiguous bytes) per chunk; the
       // first chunk is requested before the accumulator is waited for
       const long long grow = (long long)mt * BM + row;
-      const uint4* res_row = (a.res && grow < a.M) ? reinterpret_cast<const uint4*>(a.res + grow * a.ldr + nt * BN) : nullptr;
+      const uint4* res_row = (a.res && grow < a.M)
+                                 ? reinterpret_cast<const uint4*>(a.res + grow * a.ldr + nt * BN + half * kHalfN) : nullptr;
       uint4 rq[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
       if (res_row) {
 #pragma unroll
@@ -194,17 +202,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // staging tile of the previous store must have been read by the TMA engine
       if (et == 0) tma_store_wait_read<0>();
       named_bar_sync(1, kEpiThreads);
-      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN) + ((uint32_t)(lane_grp * 32) << 16);
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN + half * kHalfN) + ((uint32_t)(lane_grp * 32) << 16);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
+      for (int cc = 0; cc < kHalfN; cc += 32) {
+        const int c0 = half * kHalfN + cc;                     // first column of this chunk within the tile
         uint32_t v[32];
         // the addend of the NEXT 32 columns is requested now, a whole chunk ahead of its use
         uint4 rn[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (res_row && c0 + 32 < BN) {
+        if (res_row && cc + 32 < kHalfN) {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) rn[q] = __ldg(res_row + (c0 + 32) / 8 + q);
+          for (int q = 0; q < 4; ++q) rn[q] = __ldg(res_row + (cc + 32) / 8 + q);
         }
-        tmem_ld_32x32b_x32(taddr + c0, v);
+        tmem_ld_32x32b_x32(taddr + cc, v);
         tmem_ld_wait();
         if (res_row) {
 #pragma unroll
@@ -243,21 +252,31 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int p = 0; p < C::kPanels; ++p) tma_store_2d(&tmD, staging + (size_t)p * (BM * 128), nt * BN + p * 64, mt * BM);
         tma_store_commit();
       }
-      // per-column statistics of the rounded tile (rows beyond M were zero-filled by TMA: they add nothing)
+      // per-column statistics of the rounded tile (rows beyond M were zero-filled by TMA: they add nothing).  A work
+      // item is (column pair, row part): one 32-bit shared-memory load yields two columns of a row, consecutive threads
+      // take consecutive column pairs (conflict-free whatever the swizzle: the 32 words of a warp lie in one 128-byte row)
       if (a.colsum) {
-        for (int col = et; col < BN; col += kEpiThreads) {
+        constexpr int kPairs = BN / 2;                          // column pairs per tile
+        constexpr int kParts = kEpiThreads / kPairs >= 1 ? kEpiThreads / kPairs : 1;   // row parts (BN = 256: 2, 128: 4, 64: 8)
+        constexpr int kRows = BM / kParts;
+        for (int idx = et; idx < kPairs * kParts; idx += kEpiThreads) {
+          const int pair = idx % kPairs, part = idx / kPairs;
+          const int col = 2 * pair;
           const uint8_t* panel = staging + (size_t)(col >> 6) * (BM * 128);
           const int chunk = (col & 63) >> 3, within = (col & 7) * 2;
-          float s1 = 0.f, s2 = 0.f;
+          float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
 #pragma unroll 8
-          for (int r = 0; r < BM; ++r) {
-            const __nv_bfloat16 h = *reinterpret_cast<const __nv_bfloat16*>(panel + r * 128 + ((chunk ^ (r & 7)) << 4) + within);
-            const float f = __bfloat162float(h);
-            s1 += f;
-            s2 = fmaf(f, f, s2);
+          for (int rr = 0; rr < kRows; ++rr) {
+            const int r = part * kRows + rr;
+            const uint32_t h2 = *reinterpret_cast<const uint32_t*>(panel + r * 128 + ((chunk ^ (r & 7)) << 4) + within);
+            const float fa = bf16_lo(h2), fb = bf16_hi(h2);
+            s1a += fa; s1b += fb;
+            s2a = fmaf(fa, fa, s2a); s2b = fmaf(fb, fb, s2b);
           }
-          atomicAdd(&a.colsum[nt * BN + col], s1);
-          atomicAdd(&a.colsq[nt * BN + col], s2);
+          atomicAdd(&a.colsum[nt * BN + col], s1a);
+          atomicAdd(&a.colsum[nt * BN + col + 1], s1b);
+          atomicAdd(&a.colsq[nt * BN + col], s2a);
+          atomicAdd(&a.colsq[nt * BN + col + 1], s2b);
         }
       }
     }

@@ -3,9 +3,10 @@
 // The step's launch list (profiles/r01_step_launches_final.txt) had the cuDNN stem convolution at 9.6 % of the step
 // (one launch, 11 ms for 1024 frames: 3 input channels do not feed an implicit-GEMM kernel), its weight gradient at
 // 2.6 % and ATen's max-pool pair at 8.9 %.  Here:
-//   * stem_im2col: the 7x7x3 patches of every output pixel as rows of a (F*Ho*Wo, 192) bf16 matrix, K ordered
-//     (kh, kw, c) -- in an NHWC image with 3 channels the 21 values of one kernel row are 21 CONTIGUOUS elements --
-//     zero padded from 147 to 192 so that the tcgen05 GEMMs of this library take it as a 1x1 convolution:
+//   * stem_im2col: the 7x7x3 patches of every output pixel as rows of a (F*Ho*Wo, 192) bf16 matrix, column
+//     k = kh*24 + kw*3 + c -- in an NHWC image with 3 channels the 21 values of one kernel row are 21 CONTIGUOUS
+//     elements; each kernel row is padded to 24 columns (three aligned 16-byte chunks) and the matrix to 192 columns
+//     so that the tcgen05 GEMMs of this library take it as a 1x1 convolution:
 //     conv1x1_gemm gives the convolution (with the BatchNorm statistics in its epilogue), conv1x1_wgrad its
 //     weight gradient.  The input needs no gradient.
 //   * maxpool3x3s2_fwd / _bwd: NHWC bf16, 8 channels per thread; the forward records the arg-max position inside the
@@ -22,11 +23,17 @@ namespace mvfb {
 
 namespace {
 
-constexpr int kStemK = 147, kStemKp = 192;
+constexpr int kStemKp = 192;       // row length of the patch matrix: 8 groups of 24 columns
+constexpr int kRowK = 24;          // one kernel row kh = 21 values (kw, c) + 3 zeros: 48 bytes = three aligned 16-byte chunks
 
-// x: (F, H, W, 3) bf16 NHWC.  One thread per (output pixel, 8-element chunk of the 192-wide row).
+// x: (F, H, W, 3) bf16 NHWC.  One thread per (output pixel, 16-byte chunk of the 192-wide row); column
+// k = kh*24 + kw*3 + c (kw*3 + c < 21), the rest zero.  The 8 values of a chunk are 8 CONSECUTIVE elements of input
+// row ih = 2*oh - 3 + kh starting at element (2*ow - 3)*3 + 8*j -- an odd element index, i.e. a 2-byte-aligned
+// address: the interior fast path reads the five aligned 32-bit words around them and funnel-shifts (5 loads and
+// 4 shifts per 16 bytes written instead of 8 two-byte loads and 7 merges; the first version gathered element by
+// element and ran at 23 % of the HBM rate, profiles/r02_bench_a_b160.json).  Image borders take the element loop.
 // I = index type of the flattened work item: unsigned 32-bit whenever the launch has fewer than 2^31 items (64-bit
-// division / modulo costs ~100 instructions each and made these kernels instruction-bound: im2col 3.7 ms)
+// division / modulo costs ~100 instructions each).
 template <typename I>
 __global__ void __launch_bounds__(256)
 stem_im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ a, int H, int W, int Ho, int Wo,
@@ -40,21 +47,32 @@ stem_im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
   const int oh = (int)(t % (I)Ho);
   const long long f = (long long)(t / (I)Ho);
   const int rowlen = W * 3;
-  const int e0 = (2 * ow - 3) * 3;                              // element offset of kw = 0, c = 0 inside an image row
-  const unsigned short* img = reinterpret_cast<const unsigned short*>(x) + f * (long long)H * rowlen;
-  unsigned short v[8];
+  const int kh = chunk / 3, j = chunk - kh * 3;
+  const int ih = 2 * oh - 3 + kh;
+  uint4 o = make_uint4(0u, 0u, 0u, 0u);
+  if (kh < 7 && ih >= 0 && ih < H) {
+    const int off = (2 * ow - 3) * 3 + 8 * j;                    // first element of the chunk inside image row ih
+    const unsigned short* src = reinterpret_cast<const unsigned short*>(x) + (f * H + ih) * (long long)rowlen;
+    if (!(W & 1) && off >= 1 && off + 9 <= rowlen) {
+      // off is odd: the elements off-1 .. off+8 are five aligned words
+      const uint32_t* wp = reinterpret_cast<const uint32_t*>(src + off - 1);
+      const uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
+      o.x = __funnelshift_r(w0, w1, 16);
+      o.y = __funnelshift_r(w1, w2, 16);
+      o.z = __funnelshift_r(w2, w3, 16);
+      o.w = __funnelshift_r(w3, w4, 16);
+      if (j == 2) { o.z &= 0xffffu; o.w = 0u; }                  // values 21..23 of the kernel row do not exist
+    } else {
+      unsigned short v[8];
 #pragma unroll
-  for (int e = 0; e < 8; ++e) {
-    const int k = chunk * 8 + e;
-    const int kh = k / 21, r = k - kh * 21;                     // k = (kh*7 + kw)*3 + c
-    const int ih = 2 * oh - 3 + kh, off = e0 + r;
-    unsigned short val = 0;
-    if (k < kStemK && ih >= 0 && ih < H && off >= 0 && off < rowlen) val = __ldg(img + (long long)ih * rowlen + off);
-    v[e] = val;
+      for (int e = 0; e < 8; ++e) {
+        const int r = 8 * j + e, q = off + e;
+        v[e] = (r < 21 && q >= 0 && q < rowlen) ? __ldg(src + q) : (unsigned short)0;
+      }
+      o.x = v[0] | ((uint32_t)v[1] << 16); o.y = v[2] | ((uint32_t)v[3] << 16);
+      o.z = v[4] | ((uint32_t)v[5] << 16); o.w = v[6] | ((uint32_t)v[7] << 16);
+    }
   }
-  uint4 o;
-  o.x = v[0] | ((uint32_t)v[1] << 16); o.y = v[2] | ((uint32_t)v[3] << 16);
-  o.z = v[4] | ((uint32_t)v[5] << 16); o.w = v[6] | ((uint32_t)v[7] << 16);
   reinterpret_cast<uint4*>(a)[i] = o;
 }
 

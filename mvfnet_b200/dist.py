@@ -54,6 +54,18 @@ class FlatGrads:
                 off += p.numel()
             self.buffers[key], self.views[key] = flat, views
 
+    def restride(self, params):
+        """Give every flat view its parameter's own (dense) strides -- FlatSGD moves channels_last weights into flat
+        memory in their own element order, and its elementwise update must pair gradient i with parameter i."""
+        for key, ps in self.groups.items():
+            flat, views, off = self.buffers[key], [], 0
+            for p in ps:
+                dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
+                v = flat[off:off + p.numel()]
+                views.append(v.as_strided(p.shape, p.stride()) if dense else v.view(p.shape))
+                off += p.numel()
+            self.views[key] = views
+
     def zero_(self):
         """Replaces optimizer.zero_grad(): no kernel at all."""
         for p in self.params:
@@ -74,8 +86,6 @@ class FlatGrads:
                 torch._foreach_copy_(dst, src)
             for p, v in zip(ps, views):
                 p.grad = v
-
-    check_views = gather                        # older call sites
 
     def numel(self):
         return sum(f.numel() for f in self.buffers.values())

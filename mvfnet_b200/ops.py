@@ -81,40 +81,80 @@ def _stream():
 
 _T = _mvf._Timed          # bench.py's per-family launch timing (no-op unless mvf.timing_begin() was called)
 
-# (id(param), form) -> (weak reference to the parameter, its version, tensor).  `Tensor._version` is bumped by every
-# in-place update (the optimizer step), so a stale form is never used, and the weak reference guards against a dead
-# parameter's id being re-used by another tensor.  Forms:
-#   "rows"  (Cout, Cin*kh*kw) bf16                     1x1 forward operand B
-#   "rowsT" (Cin, Cout) bf16                           1x1 input-gradient operand B (= W^T)
-#   "krsc"  (Cout, 3, 3, Cin) bf16                     3x3 forward operand B
-#   "rot"   (Cin, 3, 3, Cout) bf16, taps rotated 180   3x3 stride-1 input-gradient operand B
-#   "nchw"  (Cout, Cin, kh, kw) bf16                   library fallbacks
+# (id(param), form) -> (weak reference to the parameter, its version, weight epoch, tensor).  `Tensor._version` is
+# bumped by every in-place torch update, `_WEIGHT_EPOCH` by FlatSGD.step() (whose kernel updates the flat parameter
+# buffer behind autograd's back), so a stale form is never used; the weak reference guards against a dead parameter's id
+# being re-used by another tensor.  Forms:
+#   "rows"   (Cout, Cin*kh*kw) bf16                     1x1 forward operand B
+#   "rowsT"  (Cin, Cout) bf16                           1x1 input-gradient operand B (= W^T)
+#   "nchw"   (Cout, Cin, kh, kw) bf16 in the parameter's memory format
+#   "krsc"   (Cout, 3, 3, Cin) bf16 contiguous          3x3 forward operand B (a no-op view for channels_last weights)
+#   "rot"    (Cin, 3, 3, Cout) bf16, taps rotated 180   3x3 stride-1 input-gradient operand B
+#   "fcpad"  (ceil64(NC), K) bf16, zero rows appended   classification head: classes padded to the GEMM's N granularity
+#   "fcpadT" (K, ceil64(NC)) bf16                       ... its input-gradient operand
 _WFORMS = {}
+_WEIGHT_EPOCH = 0
+# id(param) -> (weak reference, bf16 view of the parameter kept current by FlatSGD's update kernel)
+_BF16_SOURCES = {}
+
+
+def bump_weight_epoch():
+    global _WEIGHT_EPOCH
+    _WEIGHT_EPOCH += 1
+
+
+def register_bf16_sources(params, views):
+    """FlatSGD: `views[i]` is a bf16 tensor of params[i]'s shape and strides that its step kernel rewrites together with
+    the fp32 parameter -- the "nchw" / "rows" forms become views of it (no cast kernel per layer per step)."""
+    for p, v in zip(params, views):
+        _BF16_SOURCES[id(p)] = (weakref.ref(p), v)
+    bump_weight_epoch()
+
+
+def _bf16_source(weight):
+    hit = _BF16_SOURCES.get(id(weight))
+    if hit is not None and hit[0]() is weight and hit[1].device == weight.device:
+        return hit[1]
+    return None
 
 
 def _wform(weight, form):
     key = (id(weight), form)
     ver = weight._version
     hit = _WFORMS.get(key)
-    if hit is not None and hit[0]() is weight and hit[1] == ver and hit[2].device == weight.device:
-        return hit[2]
-    w = weight.detach()
-    if form == "rows":
-        t = w.reshape(w.shape[0], -1).to(torch.bfloat16)
+    if (hit is not None and hit[0]() is weight and hit[1] == ver and hit[2] == _WEIGHT_EPOCH
+            and hit[3].device == weight.device):
+        return hit[3]
+    if form == "nchw":
+        t = _bf16_source(weight)
+        if t is None:
+            t = weight.detach().to(torch.bfloat16)
+    elif form == "rows":
+        w = _wform(weight, "nchw")
+        t = w.reshape(w.shape[0], -1)
+        if t.stride(1) != 1:                                     # a channels_last k x k weight viewed as rows
+            t = t.contiguous()
     elif form == "rowsT":
         t = _wform(weight, "rows").t().contiguous()
-    elif form == "nchw":
-        t = w.to(torch.bfloat16)
     elif form == "krsc":
         t = _wform(weight, "nchw").permute(0, 2, 3, 1).contiguous()
     elif form == "rot":
         t = _wform(weight, "nchw").flip(2, 3).permute(1, 2, 3, 0).contiguous()
+    elif form == "fcpad":
+        w = _wform(weight, "rows")
+        npad = (w.shape[0] + 63) // 64 * 64
+        t = torch.zeros((npad, w.shape[1]), dtype=torch.bfloat16, device=w.device)
+        t[:w.shape[0]] = w
+    elif form == "fcpadT":
+        t = _wform(weight, "fcpad").t().contiguous()
     else:
         raise KeyError(form)
     if len(_WFORMS) > 4096:                                    # models that came and went (test suites)
         for k in [k for k, v in _WFORMS.items() if v[0]() is None]:
             del _WFORMS[k]
-    _WFORMS[key] = (weakref.ref(weight), ver, t)
+        for k in [k for k, v in _BF16_SOURCES.items() if v[0]() is None]:
+            del _BF16_SOURCES[k]
+    _WFORMS[key] = (weakref.ref(weight), ver, _WEIGHT_EPOCH, t)
     return t
 
 
@@ -440,7 +480,14 @@ def conv3x3(x, weight, stride=1, stats=False):
 
 # ------------------------------------------------------------------------------------------------ BatchNorm
 # ---------------------------------------------------------------------------------------------- stem
-STEM_K, STEM_KP = 147, 192
+STEM_KP = 192             # patch-matrix row: column kh*24 + kw*3 + c (21 values + 3 zeros per kernel row, 8 groups)
+
+
+def _stem_weight_matrix(weight):
+    """(64, 3, 7, 7) -> the (64, 192) bf16 B operand in stem_im2col's column order."""
+    wm = torch.zeros((weight.shape[0], 8, 24), dtype=torch.bfloat16, device=weight.device)
+    wm[:, :7, :21] = weight.detach().permute(0, 2, 3, 1).reshape(weight.shape[0], 7, 21)
+    return wm.view(weight.shape[0], STEM_KP)
 
 
 def stem_enabled() -> bool:
@@ -469,9 +516,7 @@ class _StemConv(torch.autograd.Function):
         a = torch.empty((f * ho * wo, STEM_KP), dtype=torch.bfloat16, device=x.device)
         with _T("stem_im2col", nbytes=2 * (xb.numel() + a.numel())):
             _lib.check(L.stem_im2col(ptr(xb), ptr(a), f, h, w, _stream()), "stem_im2col")
-        wm = torch.zeros((64, STEM_KP), dtype=torch.bfloat16, device=x.device)
-        wm[:, :STEM_K] = weight.detach().permute(0, 2, 3, 1).reshape(64, STEM_K)           # K order (kh, kw, c)
-        out, colsum, _ = gemm_tn(a, wm, stats=stats)
+        out, colsum, _ = gemm_tn(a, _stem_weight_matrix(weight), stats=stats)
         ctx.save_for_backward(a)
         ctx.wdtype = weight.dtype
         y = _nhwc_from_rows(out, f, ho, wo)
@@ -487,7 +532,7 @@ class _StemConv(torch.autograd.Function):
         dw = None
         if ctx.needs_input_grad[1]:
             g2 = _rows(g.contiguous(memory_format=torch.channels_last))
-            dw = gemm_wgrad(g2, a)[:, :STEM_K].reshape(64, 7, 7, 3).permute(0, 3, 1, 2).to(ctx.wdtype)
+            dw = gemm_wgrad(g2, a).view(64, 8, 24)[:, :7, :21].reshape(64, 7, 7, 3).permute(0, 3, 1, 2).to(ctx.wdtype)
         return None, dw, None
 
 

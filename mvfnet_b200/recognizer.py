@@ -85,8 +85,13 @@ class Recognizer2D(BaseRecognizer):
         losses = dict()
         if self.with_cls_head:
             temporal_pool = imgs.shape[0] // x.shape[0]
-            cls_score = self.cls_head(x, num_seg // temporal_pool)
-            losses.update(self.cls_head.loss(cls_score.float(), labels.squeeze()))
+            from . import tail
+            if tail.head_loss_eligible(x, self.cls_head, labels):
+                # pool -> dropout -> Linear -> consensus -> cross-entropy on the library's kernels (tail.py)
+                losses['loss_cls'] = tail.head_loss(x, self.cls_head, labels, num_seg // temporal_pool)
+            else:
+                cls_score = self.cls_head(x, num_seg // temporal_pool)
+                losses.update(self.cls_head.loss(cls_score.float(), labels.squeeze()))
         return losses
 
     def forward_test(self, imgs, return_numpy, **kwargs):

@@ -231,6 +231,56 @@ def model_case_224(depth=50, t=8, b=2, px=224, seed=3):
     return rec
 
 
+def tail_cases(seed=400):
+    """The ends of the step, from the reference's own classes: Normalize + FormatShape (datasets/pipelines), TSNClsHead +
+    BaseHead.loss (models/heads), and clip_grad_norm_ + torch.optim.SGD in DistOptimizerHook's order (core/dist_utils.py)."""
+    with contextlib.redirect_stdout(io.StringIO()):
+        from codes.datasets.pipelines.augmentations import Normalize
+        from codes.datasets.pipelines.formating import FormatShape
+        from codes.models.heads.tsn_clshead import TSNClsHead
+    rng = np.random.RandomState(seed)
+    rec = {}
+    # -- input pipeline (config r50_dense.py:70-75)
+    mean, std = [123.675, 116.28, 103.53], [58.395, 57.12, 57.375]
+    frames = rng.randint(0, 256, (8, 6, 8, 3)).astype(np.uint8)
+    r = Normalize(mean=mean, std=std, div_255=False, to_rgb=True)(dict(img_group=[f.copy() for f in frames], modality="RGB"))
+    r.update(num_clips=1, clip_len=4)
+    rec["norm/frames"], rec["norm/mean"], rec["norm/std"] = frames, np.array(mean), np.array(std)
+    rec["norm/out"] = FormatShape("NCHW")(r)["img_group"]
+    # -- head + loss (fp64, dropout off: the reference's dropout mask is torch's RNG stream)
+    g = torch.Generator().manual_seed(seed)
+    nb, t, c, nc = 3, 4, 64, 10
+    with contextlib.redirect_stdout(io.StringIO()):
+        h = TSNClsHead(spatial_size=-1, spatial_type="avg", with_avg_pool=False, temporal_feature_size=1,
+                       spatial_feature_size=1, dropout_ratio=0.0, in_channels=c, init_std=0.01, num_classes=nc).double()
+    with torch.no_grad():
+        h.new_fc.weight.copy_(gen(h.new_fc.weight.shape, g, 0.3))
+        h.new_fc.bias.copy_(gen(h.new_fc.bias.shape, g, 0.5))
+    x = gen((nb * t, c, 3, 3), g).requires_grad_(True)
+    labels = torch.randint(0, nc, (nb, 1), generator=g)
+    loss = h.loss(h(x, t), labels.squeeze())["loss_cls"]
+    loss.backward()
+    rec.update({"head/x": x.detach().numpy(), "head/w": h.new_fc.weight.detach().numpy(), "head/b": h.new_fc.bias.detach().numpy(),
+                "head/labels": labels.numpy(), "head/T": np.array(t), "head/loss": np.array(loss.item()),
+                "head/dx": x.grad.numpy(), "head/dw": h.new_fc.weight.grad.numpy(), "head/db": h.new_fc.bias.grad.numpy()})
+    # -- optimizer tail: two steps of (sum over 2 ranks) / 2 -> clip 40 -> SGD nesterov (r50_dense.py:152-154)
+    shapes = [(7, 5), (11,), (3, 2, 2, 2)]
+    ps = [torch.nn.Parameter(gen(sh, g)) for sh in shapes]
+    opt = torch.optim.SGD(ps, lr=0.015, momentum=0.9, weight_decay=1e-4, nesterov=True)
+    rec["sgd/p0"] = np.concatenate([p_.detach().numpy().ravel() for p_ in ps])
+    for step in range(2):
+        gs = [gen(sh, g, 30.0 if step == 0 else 0.5) for sh in shapes]          # step 0 clips, step 1 does not
+        rec["sgd/g%d" % step] = np.concatenate([gi.numpy().ravel() for gi in gs])
+        for p_, gi in zip(ps, gs):
+            p_.grad = gi / 2.0                                                  # _allreduce_coalesced: / world_size
+        total = torch.nn.utils.clip_grad_norm_(ps, max_norm=40, norm_type=2)
+        opt.step()
+        rec["sgd/norm%d" % step] = np.array(float(total))
+        rec["sgd/p%d" % (step + 1)] = np.concatenate([p_.detach().numpy().ravel() for p_ in ps])
+    rec["sgd/shapes"] = np.array([",".join(map(str, sh)) for sh in shapes])
+    return rec
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(max(1, os.cpu_count() or 1))
@@ -244,6 +294,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "bottleneck_cases.npz"), **recs)
     np.savez_compressed(os.path.join(OUT, "model_r50.npz"), **model_case(50, 4, 2, 64, 0))
     np.savez_compressed(os.path.join(OUT, "model_r50_224.npz"), **model_case_224())
+    np.savez_compressed(os.path.join(OUT, "tail_cases.npz"), **tail_cases())
     # structural known-answers (config docstrings r50_dense.py:1-5 / r101_dense.py:1-5)
     counts = {}
     for depth in (50, 101):

@@ -336,3 +336,67 @@ def bottleneck_backward(dout, x, p, stride, training, cache, n_segment=None, mvf
     else:
         dx = dx + dpre
     return dx, g
+
+
+# --------------------------------------------------------------------------------------------
+# The ends of the step; pinned by tests/golden/tail_cases.npz
+# --------------------------------------------------------------------------------------------
+def normalize_format(frames_u8, mean, std, to_rgb=True):
+    """Normalize + FormatShape('NCHW') of the data pipeline (datasets/pipelines/augmentations.py:343-396,
+    formating.py:134-185): frames (M, H, W, 3) uint8 -> (M, 3, H, W) float32, (float32(x) [BGR -> RGB] - mean) * (1 / std)
+    with the channel statistics applied AFTER the optional swap, as cv2.subtract / cv2.multiply do in place."""
+    x = frames_u8.astype(np.float32)
+    if to_rgb:
+        x = x[..., ::-1]
+    # Normalize.__init__ stores mean / std as float32 (augmentations.py:357-358); imnormalize widens THOSE to float64
+    mean = np.asarray(mean, dtype=np.float32).astype(np.float64).reshape(1, 1, 1, 3)
+    stdinv = 1.0 / np.asarray(std, dtype=np.float32).astype(np.float64).reshape(1, 1, 1, 3)
+    y = ((x.astype(np.float64) - mean).astype(np.float32).astype(np.float64) * stdinv).astype(np.float32)
+    return np.ascontiguousarray(y.transpose(0, 3, 1, 2))
+
+
+def head_loss(x, w, b, labels, num_seg, keep=None, p=0.0):
+    """TSNClsHead.forward + BaseHead.loss and their gradients (heads/tsn_clshead.py:71-98, heads/base.py:40-45,
+    segmental_consensuses/simple_consensus.py:41-61): x (F, C, h, w) -> adaptive average pool -> dropout (keep mask
+    (F, C) given, scaled by 1/(1-p)) -> Linear(w (NC, C), b) -> mean over the num_seg frames of a clip -> mean
+    cross-entropy over the clips.  Returns dict(loss, score, dx, dw, db)."""
+    f, c, h, wd = x.shape
+    nb = f // num_seg
+    feat = x.mean(axis=(2, 3))
+    scale = np.ones_like(feat) if keep is None else keep.astype(x.dtype) / (1.0 - p)
+    fd = feat * scale
+    logits = fd @ w.T + b
+    score = logits.reshape(nb, num_seg, -1).mean(axis=1)
+    m = score.max(axis=1, keepdims=True)
+    lse = m[:, 0] + np.log(np.exp(score - m).sum(axis=1))
+    lab = np.asarray(labels).reshape(-1)
+    loss = float((lse - score[np.arange(nb), lab]).mean())
+    soft = np.exp(score - lse[:, None])
+    ds = soft.copy()
+    ds[np.arange(nb), lab] -= 1.0
+    ds /= nb
+    dlogits = np.repeat(ds / num_seg, num_seg, axis=0)
+    dw = dlogits.T @ fd
+    db = dlogits.sum(axis=0)
+    dfeat = (dlogits @ w) * scale
+    dx = np.broadcast_to((dfeat / (h * wd))[:, :, None, None], x.shape).copy()
+    return dict(loss=loss, score=score, dx=dx, dw=dw, db=db)
+
+
+def sgd_step(p, m, g, lr, momentum, weight_decay, nesterov, max_norm=None, world=1):
+    """DistOptimizerHook.after_train_iter after the all-reduce (core/dist_utils.py:29-32, 59-67): g is the SUM over
+    ranks; / world, clip_grad_norm_(max_norm, 2) over ALL parameters (lists of arrays), then torch.optim.SGD with a
+    zero-initialised momentum buffer.  Returns (new p list, new m list, total norm)."""
+    g = [gi / world for gi in g]
+    total = float(np.sqrt(sum(float((gi.astype(np.float64) ** 2).sum()) for gi in g)))
+    if max_norm is not None:
+        coef = min(1.0, max_norm / (total + 1e-6))
+        g = [gi * coef for gi in g]
+    newp, newm = [], []
+    for pi, mi, gi in zip(p, m, g):
+        gi = gi + weight_decay * pi
+        mi = momentum * mi + gi
+        gi = gi + momentum * mi if nesterov else mi
+        newp.append(pi - lr * gi)
+        newm.append(mi)
+    return newp, newm, total

@@ -139,3 +139,35 @@ def test_whole_model_port_vs_reference():
         if k.startswith("grad."):
             np.testing.assert_allclose(m.p[k[5:]].grad.numpy(), z[k], rtol=5e-3, atol=1e-5 * np.abs(z[k]).max())
     np.testing.assert_allclose(m.p["backbone.layer4.2.conv1.bn.running_mean"].numpy(), z["rm_after.layer4.2.conv1.bn"], rtol=1e-3, atol=1e-6)
+
+
+TAIL = load_cases("tail_cases.npz")
+
+
+def test_tail_normalize_format_vs_reference_pipeline():
+    """Normalize + FormatShape of the reference's data pipeline (augmentations.py:343-396, formating.py:134-185)."""
+    c = TAIL["norm"]
+    out = O.normalize_format(c["frames"], c["mean"], c["std"], to_rgb=True)
+    assert out.shape == c["out"].shape and out.dtype == np.float32
+    assert np.array_equal(out, c["out"])                                 # bit-exact restatement of cv2's in-place arithmetic
+
+
+def test_tail_head_loss_vs_reference_head():
+    """TSNClsHead.forward + BaseHead.loss and autograd's gradients (tsn_clshead.py:71-98, heads/base.py:40-45)."""
+    c = TAIL["head"]
+    r = O.head_loss(c["x"], c["w"], c["b"], c["labels"], int(c["T"]))
+    assert abs(r["loss"] - float(c["loss"])) < 1e-12
+    np.testing.assert_allclose(r["dx"], c["dx"], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(r["dw"], c["dw"], rtol=1e-10, atol=1e-14)
+    np.testing.assert_allclose(r["db"], c["db"], rtol=1e-10, atol=1e-14)
+
+
+def test_tail_sgd_step_vs_torch_in_hook_order():
+    """/ world -> clip_grad_norm_(40) -> SGD(momentum 0.9, wd 1e-4, nesterov) (dist_utils.py:59-67, r50_dense.py:152-154)."""
+    c = TAIL["sgd"]
+    p, m = [c["p0"].copy()], [np.zeros_like(c["p0"])]
+    for step in range(2):
+        p, m, total = O.sgd_step(p, m, [c["g%d" % step]], 0.015, 0.9, 1e-4, True, max_norm=40, world=2)
+        assert abs(total - float(c["norm%d" % step])) < 1e-9 * total
+        np.testing.assert_allclose(p[0], c["p%d" % (step + 1)], rtol=1e-12, atol=1e-14)
+    assert float(c["norm0"]) > 40 > float(c["norm1"])        # the first step clips, the second does not
