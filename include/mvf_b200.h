@@ -149,6 +149,15 @@ int conv1x1_gemm(const mvfb_gemm_desc* d, const void* a0, const void* a1, const 
 int conv1x1_gemm_add(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, const void* res,
                      long long ldr, void* out, mvfb_stream_t stream);
 
+/* Inference form of the same layers: an eval-mode BatchNorm2d (+ residual) (+ ReLU) folded into the convolution's epilogue,
+ *   out = [relu]( (A B^T)[m, n] * scale[n] + shift[n] [+ res[m*ldr + n]] ),
+ * scale = gamma / sqrt(running_var + eps), shift = beta - running_mean * scale (fp32 [N], 16-byte aligned): norm1+relu,
+ * norm2+relu, norm3 + identity + relu and the down-sample norm of Bottleneck.forward (backbones/resnet.py:213-242) under
+ * model.eval() (test_recognizer.py:72-77).  The activation makes ONE trip to HBM per convolution.
+ * conv3x3_gemm_bnact: res (optional) is (F, Ho, Wo, Cout) contiguous. */
+int conv1x1_gemm_bnact(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, const float* scale,
+                       const float* shift, const void* res, long long ldr, int relu, void* out, mvfb_stream_t stream);
+
 /* Weight gradient of the same layer: dw[n, k] = sum_m g[m*ldb + n] * X[m, k], X = [x0[:, :K0] | x1[:, K0:]] as above
  * (M = pixels, N = Cout, K = Cin; lda0 / lda1 / ldb = leading dimensions of x0 / x1 / g; dw is fp32 (N, ldd) and is
  * zeroed by the call, then accumulated with fp32 atomics over split-K partitions of the pixel axis).  Both MMA
@@ -173,6 +182,9 @@ typedef struct {
 
 int conv3x3_gemm(const mvfb_conv_desc* d, const void* x, const void* w, void* out, float* colsum, float* colsq,
                  mvfb_stream_t stream);
+
+int conv3x3_gemm_bnact(const mvfb_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
+                       const void* res, int relu, void* out, mvfb_stream_t stream);
 
 /* Its weight gradient: dw[n, r, s, c] = sum_{f,ho,wo} g[f, ho, wo, n] * x[f, ho*stride + r - 1, wo*stride + s - 1, c]
  * (g bf16 (F, Ho, Wo, Cout); dw fp32 (Cout, 3, 3, Cin), zeroed by the call; MN-major MMA operands, the x operand

@@ -46,6 +46,10 @@ struct GemmArgs {
   float* colsq;                    // [N] or null
   const __nv_bfloat16* res;        // optional (M, N) bf16 addend, leading dimension ldr: out = A B^T + res
   long long ldr;
+  // inference epilogue (eval-mode BatchNorm folded into the convolution): out = [relu]((A B^T) * ep_scale[n] + ep_shift[n] [+ res])
+  const float* ep_scale;           // [N] or null
+  const float* ep_shift;           // [N] (with ep_scale)
+  int ep_relu;
   // 3x3 convolution as an implicit GEMM (IM2COL kernels): K = 9 * Cin ordered (r, s, c); A tiles are gathered by
   // TMA im2col loads from the NHWC input, M = F * Ho * Wo output pixels
   int Cin, Ho, Wo, stride, ks, pad;   // ks = 3 (pad 1) or 1 (pad 0)
@@ -60,7 +64,9 @@ struct Cfg {
   static constexpr int kPanels = BN / 64;                     // 64-column (128 B) panels of the output tile
   static constexpr int kStagingBytes = BM * BN * 2;
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN; // power of two >= 32: BN in {64,128,256} -> 128,256,512
-  static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + kStagingBytes + 256;
+  static constexpr int kStatParts = kEpiThreads / (BN / 2);   // row parts of the statistics pass (BN = 256: 2, 128: 4, 64: 8)
+  static constexpr int kStatBytes = kStatParts * BN * 2 * 4;  // [part][sum | sumsq][BN] fp32 = 4 KB
+  static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + kStagingBytes + 256 + kStatBytes;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -82,6 +88,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   uint64_t* tmem_full = empty + C::kStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_stat = reinterpret_cast<float*>(staging + C::kStagingBytes + 256);   // [kStatParts][2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = a.K / BK;
@@ -215,6 +222,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         tmem_ld_32x32b_x32(taddr + cc, v);
         tmem_ld_wait();
+        if (a.ep_scale) {                                      // every lane reads the same 32 floats: L1 broadcast
+          const float4* sc = reinterpret_cast<const float4*>(a.ep_scale + nt * BN + c0);
+          const float4* sh = reinterpret_cast<const float4*>(a.ep_shift + nt * BN + c0);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 s4 = __ldg(sc + q), h4 = __ldg(sh + q);
+            v[4 * q + 0] = __float_as_uint(fmaf(__uint_as_float(v[4 * q + 0]), s4.x, h4.x));
+            v[4 * q + 1] = __float_as_uint(fmaf(__uint_as_float(v[4 * q + 1]), s4.y, h4.y));
+            v[4 * q + 2] = __float_as_uint(fmaf(__uint_as_float(v[4 * q + 2]), s4.z, h4.z));
+            v[4 * q + 3] = __float_as_uint(fmaf(__uint_as_float(v[4 * q + 3]), s4.w, h4.w));
+          }
+        }
         if (res_row) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -227,6 +246,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
 #pragma unroll
           for (int q = 0; q < 4; ++q) rq[q] = rn[q];
+        }
+        if (a.ep_relu) {
+#pragma unroll
+          for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(fmaxf(__uint_as_float(v[q]), 0.f));
         }
         // 32 fp32 -> 32 bf16 = 64 B = four 16-byte chunks of this row in panel c0/64
         uint8_t* panel = staging + (size_t)(c0 >> 6) * (BM * 128) + (size_t)row * 128;
@@ -257,10 +280,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // take consecutive column pairs (conflict-free whatever the swizzle: the 32 words of a warp lie in one 128-byte row)
       if (a.colsum) {
         constexpr int kPairs = BN / 2;                          // column pairs per tile
-        constexpr int kParts = kEpiThreads / kPairs >= 1 ? kEpiThreads / kPairs : 1;   // row parts (BN = 256: 2, 128: 4, 64: 8)
+        constexpr int kParts = C::kStatParts;
         constexpr int kRows = BM / kParts;
-        for (int idx = et; idx < kPairs * kParts; idx += kEpiThreads) {
-          const int pair = idx % kPairs, part = idx / kPairs;
+        {
+          const int pair = et % kPairs, part = et / kPairs;     // kPairs * kParts == kEpiThreads
           const int col = 2 * pair;
           const uint8_t* panel = staging + (size_t)(col >> 6) * (BM * 128);
           const int chunk = (col & 63) >> 3, within = (col & 7) * 2;
@@ -273,10 +296,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             s1a += fa; s1b += fb;
             s2a = fmaf(fa, fa, s2a); s2b = fmaf(fb, fb, s2b);
           }
-          atomicAdd(&a.colsum[nt * BN + col], s1a);
-          atomicAdd(&a.colsum[nt * BN + col + 1], s1b);
-          atomicAdd(&a.colsq[nt * BN + col], s2a);
-          atomicAdd(&a.colsq[nt * BN + col + 1], s2b);
+          float* mine = s_stat + (size_t)part * (2 * BN);
+          *reinterpret_cast<float2*>(mine + col) = make_float2(s1a, s1b);
+          *reinterpret_cast<float2*>(mine + BN + col) = make_float2(s2a, s2b);
+        }
+        // one atomic per column and statistic per tile: the partial sums of the row parts meet in shared memory first
+        // (atomics on one address serialise in L2; with a part per atomic the K = 64 layers were bound by them)
+        named_bar_sync(1, kEpiThreads);
+        for (int i = et; i < 2 * BN; i += kEpiThreads) {
+          float v = 0.f;
+#pragma unroll
+          for (int q = 0; q < kParts; ++q) v += s_stat[(size_t)q * (2 * BN) + i];
+          atomicAdd(i < BN ? &a.colsum[nt * BN + i] : &a.colsq[nt * BN + i - BN], v);
         }
       }
     }
@@ -319,9 +350,15 @@ int launch_kernel(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtens
   return MVFB_OK;
 }
 
+struct Epi {                       // optional inference epilogue
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+  int relu = 0;
+};
+
 template <int BN>
 int launch(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, const void* res, long long ldr,
-           void* out, float* colsum, float* colsq, cudaStream_t st) {
+           void* out, float* colsum, float* colsq, const Epi& ep, cudaStream_t st) {
   using C = Cfg<BN>;
   CUtensorMap tmA0, tmA1, tmB, tmD;
   int rc;
@@ -338,6 +375,7 @@ int launch(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* 
   a.M = d->M; a.N = d->N; a.K = d->K; a.K0 = d->K0;
   a.colsum = colsum; a.colsq = colsq;
   a.res = (const __nv_bfloat16*)res; a.ldr = ldr;
+  a.ep_scale = ep.scale; a.ep_shift = ep.shift; a.ep_relu = ep.relu;
   a.Cin = a.Ho = a.Wo = a.stride = a.pad = 0;
   a.ks = 1;
   return launch_kernel<BN, false>(tmA0, tmA1, tmB, tmD, a, st);
@@ -346,7 +384,7 @@ int launch(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* 
 // 3x3 / pad 1 convolution: A gathered by TMA im2col from x (F, H, W, Cin); B = weights (Cout, 3, 3, Cin)
 template <int BN>
 int launch_conv3x3(const mvfb_conv_desc* d, const void* x, const void* w, void* out, float* colsum, float* colsq,
-                   cudaStream_t st) {
+                   const void* res, const Epi& ep, cudaStream_t st) {
   const int Ho = (d->H - 1) / d->stride + 1, Wo = (d->W - 1) / d->stride + 1;
   CUtensorMap tmA, tmB, tmD;
   const uint64_t dims[4] = {(uint64_t)d->Cin, (uint64_t)d->W, (uint64_t)d->H, (uint64_t)d->F};
@@ -363,7 +401,8 @@ int launch_conv3x3(const mvfb_conv_desc* d, const void* x, const void* w, void* 
   GemmArgs a;
   a.M = M; a.N = d->Cout; a.K = taps * d->Cin; a.K0 = 0;
   a.colsum = colsum; a.colsq = colsq;
-  a.res = nullptr; a.ldr = 0;
+  a.res = (const __nv_bfloat16*)res; a.ldr = d->Cout;
+  a.ep_scale = ep.scale; a.ep_shift = ep.shift; a.ep_relu = ep.relu;
   a.Cin = d->Cin; a.Ho = Ho; a.Wo = Wo; a.stride = d->stride; a.ks = d->ksize; a.pad = pad;
   return launch_kernel<BN, true>(tmA, tmA, tmB, tmD, a, st);
 }
@@ -375,7 +414,7 @@ int launch_conv3x3(const mvfb_conv_desc* d, const void* x, const void* w, void* 
 using namespace mvfb;
 
 static int conv1x1_gemm_impl(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, const void* res,
-                             long long ldr, void* out, float* colsum, float* colsq, mvfb_stream_t stream) {
+                             long long ldr, void* out, float* colsum, float* colsq, const Epi& ep, mvfb_stream_t stream) {
   MVFB_CHECK(d && a1 && b && out, MVFB_ERR_ARG, "null descriptor / operand");
   MVFB_CHECK(d->M > 0 && d->N > 0 && d->K > 0, MVFB_ERR_ARG, "bad GEMM shape M=%lld N=%d K=%d", d->M, d->N, d->K);
   MVFB_CHECK(d->K % BK == 0 && d->K0 % BK == 0 && d->K0 >= 0 && d->K0 < d->K, MVFB_ERR_UNSUPPORTED,
@@ -390,34 +429,60 @@ static int conv1x1_gemm_impl(const mvfb_gemm_desc* d, const void* a0, const void
   MVFB_CHECK(!res || (!((uintptr_t)res & 15) && ldr % 8 == 0 && ldr >= d->N), MVFB_ERR_UNSUPPORTED,
              "the addend must be 16-byte aligned with a leading dimension that is a multiple of 8 and >= N");
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->N % 256 == 0) return launch<256>(d, a0, a1, b, res, ldr, out, colsum, colsq, st);
-  if (d->N % 128 == 0) return launch<128>(d, a0, a1, b, res, ldr, out, colsum, colsq, st);
-  return launch<64>(d, a0, a1, b, res, ldr, out, colsum, colsq, st);
+  MVFB_CHECK(!ep.scale || (ep.shift && !((uintptr_t)ep.scale & 15) && !((uintptr_t)ep.shift & 15)), MVFB_ERR_ARG,
+             "the epilogue scale needs a shift, both 16-byte aligned");
+  if (d->N % 256 == 0) return launch<256>(d, a0, a1, b, res, ldr, out, colsum, colsq, ep, st);
+  if (d->N % 128 == 0) return launch<128>(d, a0, a1, b, res, ldr, out, colsum, colsq, ep, st);
+  return launch<64>(d, a0, a1, b, res, ldr, out, colsum, colsq, ep, st);
 }
 
 extern "C" int conv1x1_gemm(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, void* out,
                             float* colsum, float* colsq, mvfb_stream_t stream) {
-  return conv1x1_gemm_impl(d, a0, a1, b, nullptr, 0, out, colsum, colsq, stream);
+  return conv1x1_gemm_impl(d, a0, a1, b, nullptr, 0, out, colsum, colsq, Epi{}, stream);
 }
 
 extern "C" int conv1x1_gemm_add(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, const void* res,
                                 long long ldr, void* out, mvfb_stream_t stream) {
   MVFB_CHECK(res != nullptr, MVFB_ERR_ARG, "conv1x1_gemm_add needs the addend");
-  return conv1x1_gemm_impl(d, a0, a1, b, res, ldr, out, nullptr, nullptr, stream);
+  return conv1x1_gemm_impl(d, a0, a1, b, res, ldr, out, nullptr, nullptr, Epi{}, stream);
 }
 
-extern "C" int conv3x3_gemm(const mvfb_conv_desc* d, const void* x, const void* w, void* out, float* colsum,
-                            float* colsq, mvfb_stream_t stream) {
+extern "C" int conv1x1_gemm_bnact(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, const float* scale,
+                                  const float* shift, const void* res, long long ldr, int relu, void* out,
+                                  mvfb_stream_t stream) {
+  MVFB_CHECK(scale && shift, MVFB_ERR_ARG, "conv1x1_gemm_bnact needs scale and shift");
+  Epi ep;
+  ep.scale = scale; ep.shift = shift; ep.relu = relu;
+  return conv1x1_gemm_impl(d, a0, a1, b, res, ldr, out, nullptr, nullptr, ep, stream);
+}
+
+static int conv3x3_gemm_impl(const mvfb_conv_desc* d, const void* x, const void* w, void* out, float* colsum,
+                             float* colsq, const void* res, const Epi& ep, mvfb_stream_t stream) {
   MVFB_CHECK(d && x && w && out, MVFB_ERR_ARG, "null descriptor / operand");
   MVFB_CHECK(d->F > 0 && d->H > 0 && d->W > 0 && (d->stride == 1 || d->stride == 2) && (d->ksize == 3 || d->ksize == 1),
              MVFB_ERR_ARG, "bad conv shape F=%d H=%d W=%d stride=%d ksize=%d", d->F, d->H, d->W, d->stride, d->ksize);
   MVFB_CHECK(d->Cin % BK == 0 && d->Cout % 64 == 0, MVFB_ERR_UNSUPPORTED, "Cin=%d and Cout=%d must be multiples of 64",
              d->Cin, d->Cout);
   MVFB_CHECK((colsum == nullptr) == (colsq == nullptr), MVFB_ERR_ARG, "colsum and colsq go together");
-  MVFB_CHECK(!((uintptr_t)x & 15) && !((uintptr_t)w & 15) && !((uintptr_t)out & 15), MVFB_ERR_UNSUPPORTED,
-             "operands must be 16-byte aligned");
+  MVFB_CHECK(!((uintptr_t)x & 15) && !((uintptr_t)w & 15) && !((uintptr_t)out & 15) && !((uintptr_t)res & 15),
+             MVFB_ERR_UNSUPPORTED, "operands must be 16-byte aligned");
+  MVFB_CHECK(!ep.scale || (ep.shift && !((uintptr_t)ep.scale & 15) && !((uintptr_t)ep.shift & 15)), MVFB_ERR_ARG,
+             "the epilogue scale needs a shift, both 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->Cout % 256 == 0) return launch_conv3x3<256>(d, x, w, out, colsum, colsq, st);
-  if (d->Cout % 128 == 0) return launch_conv3x3<128>(d, x, w, out, colsum, colsq, st);
-  return launch_conv3x3<64>(d, x, w, out, colsum, colsq, st);
+  if (d->Cout % 256 == 0) return launch_conv3x3<256>(d, x, w, out, colsum, colsq, res, ep, st);
+  if (d->Cout % 128 == 0) return launch_conv3x3<128>(d, x, w, out, colsum, colsq, res, ep, st);
+  return launch_conv3x3<64>(d, x, w, out, colsum, colsq, res, ep, st);
+}
+
+extern "C" int conv3x3_gemm(const mvfb_conv_desc* d, const void* x, const void* w, void* out, float* colsum,
+                            float* colsq, mvfb_stream_t stream) {
+  return conv3x3_gemm_impl(d, x, w, out, colsum, colsq, nullptr, Epi{}, stream);
+}
+
+extern "C" int conv3x3_gemm_bnact(const mvfb_conv_desc* d, const void* x, const void* w, const float* scale,
+                                  const float* shift, const void* res, int relu, void* out, mvfb_stream_t stream) {
+  MVFB_CHECK(scale && shift, MVFB_ERR_ARG, "conv3x3_gemm_bnact needs scale and shift");
+  Epi ep;
+  ep.scale = scale; ep.shift = shift; ep.relu = relu;
+  return conv3x3_gemm_impl(d, x, w, out, nullptr, nullptr, res, ep, stream);
 }

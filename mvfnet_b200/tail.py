@@ -200,13 +200,16 @@ class FlatSGD:
         self.grads.zero_()
 
     def step(self, world=None):
+        """`world`: number of ranks the gradient is averaged over (default: the process group's size).  The all-reduce
+        runs whenever a process group of more than one rank exists; passing `world` without one (tests) only scales."""
         from .dist import get_dist_info
         import torch.distributed as dist
         L = _L()
+        ranks = get_dist_info()[1]
         if world is None:
-            world = get_dist_info()[1]
+            world = ranks
         self.grads.gather()
-        if world > 1:
+        if ranks > 1:
             dist.all_reduce(self.flat_g)                                       # the ONE collective of the step
         d = self.defaults
         n = self.flat_g.numel()

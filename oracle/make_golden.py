@@ -204,30 +204,36 @@ FULL_GRADS_224 = ("backbone.conv1.weight", "backbone.layer1.0.conv1.weight", "ba
 
 def model_case_224(depth=50, t=8, b=2, px=224, seed=3):
     """The bench configuration's geometry (T = 8, 224 px: 56/28/14/7 stage resolutions, MVF on 14x14 and 7x7 slabs) at
-    B = 2 clips, fp32, train mode: loss, every parameter's gradient norm, the full gradient of every 1-D parameter
-    (BatchNorm affine, bias), of every MVF tap tensor and of a few convolutions.  The input is NOT stored (9.6 MB):
-    it is regenerated from the seed with the CPU generator, its checksum is."""
-    with contextlib.redirect_stdout(io.StringIO()):
-        m = build_recognizer(model_cfg(depth, t, 0.0), None, dict(average_clips="prob"))
-    sd = synth_state_dict(seed, depth=depth, n_segment=t)
-    m.load_state_dict(sd)
+    B = 2 clips, train mode, in FLOAT64 (the reference model .double(): the truth that float32 / bf16 implementations
+    are measured against) on synth_state_dict(conditioned=True) weights: loss, every parameter's gradient norm, the full
+    gradient of every 1-D parameter (BatchNorm affine, bias), of every MVF tap tensor and of a few convolutions, and the
+    same quantities from the reference in float32 (its own rounding noise: the floor of any float32 comparison).
+    The input is NOT stored (9.6 MB): it is regenerated from the seed with the CPU generator, its checksum is."""
     g = torch.Generator().manual_seed(seed + 1)
     img = torch.randn((b, t, 3, px, px), generator=g)
     label = torch.randint(0, 400, (b, 1), generator=g)
     rec = {"meta": np.array([depth, t, b, px, seed]), "label": label.numpy(),
            "img_checksum": np.array([img.double().sum().item(), img.double().abs().sum().item()])}
-    m.train()
-    loss = m(img, label)["loss_cls"]
-    loss.backward()
-    rec["train_loss"] = np.array(loss.item())
-    names, norms = [], []
-    for k, p in m.named_parameters():
-        names.append(k)
-        norms.append(p.grad.double().norm().item())
-        if p.dim() == 1 or "shift_conv" in k or "h_conv" in k or "w_conv" in k or k in FULL_GRADS_224:
-            rec["grad." + k] = p.grad.numpy().copy()
+
+    def run(dtype):
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = build_recognizer(model_cfg(depth, t, 0.0), None, dict(average_clips="prob"))
+        m.load_state_dict(synth_state_dict(seed, depth=depth, n_segment=t, conditioned=True))
+        m = m.to(dtype).train()
+        loss = m(img.to(dtype), label)["loss_cls"]
+        loss.backward()
+        return loss.item(), {k: p.grad.double().numpy() for k, p in m.named_parameters()}
+
+    loss64, g64 = run(torch.float64)
+    loss32, g32 = run(torch.float32)
+    rec["train_loss"], rec["train_loss_f32"] = np.array(loss64), np.array(loss32)
+    names = list(g64)
     rec["grad_names"] = np.array(names)
-    rec["grad_norms"] = np.array(norms)
+    rec["grad_norms"] = np.array([np.linalg.norm(g64[k]) for k in names])
+    rec["f32_rel_l2"] = np.array([np.linalg.norm(g32[k] - g64[k]) / max(np.linalg.norm(g64[k]), 1e-300) for k in names])
+    for k in names:
+        if g64[k].ndim == 1 or "shift_conv" in k or "h_conv" in k or "w_conv" in k or k in FULL_GRADS_224:
+            rec["grad." + k] = g64[k].astype(np.float32)
     return rec
 
 

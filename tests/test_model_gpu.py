@@ -102,7 +102,8 @@ def _golden_224():
     chk = np.array([img.double().sum().item(), img.double().abs().sum().item()])
     np.testing.assert_allclose(chk, z["img_checksum"], rtol=1e-12, err_msg="the seeded input is not the golden run's")
     assert np.array_equal(label.numpy(), z["label"])
-    return z, depth, t, seed, img, label
+    sd = synth_state_dict(seed, depth=depth, n_segment=t, conditioned=True)
+    return z, depth, t, sd, img, label
 
 
 def _rel_l2(a, b):
@@ -110,52 +111,80 @@ def _rel_l2(a, b):
     return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
 
 
-def test_whole_model_224_fp32_gradients_vs_reference():
-    """R50 8x8 at 224 px (the bench geometry), B = 2, fp32: loss within 1e-4, EVERY stored gradient of the unmodified
-    reference (oracle/make_golden.py::model_case_224, oneDNN on the CPU) within 2e-2 relative L2 and every parameter's
-    gradient norm within 2e-2 -- the gradients of the first layers have passed through 53 train-mode BatchNorm layers
-    and ~100 ReLU masks computed by different fp32 summation orders (cuDNN / this library vs oneDNN); the measured values
-    are written to gpurun_out/fp32_model_grad_parity.json."""
+def _record(name, rec):
     import json
     import os
-    from mvfnet_b200 import build_recognizer
-    z, depth, t, seed, img, label = _golden_224()
-    m = build_recognizer(model_cfg(depth, t, 0.0), None, None)
-    m.load_state_dict(synth_state_dict(seed, depth=depth, n_segment=t))
-    m = m.cuda().train()
-    loss = m(img.cuda(), label.cuda())["loss_cls"]
-    loss.backward()
-    assert abs(loss.item() - float(z["train_loss"])) < 1e-4 * abs(float(z["train_loss"]))
-    params = dict(m.named_parameters())
-    norms = dict(zip([str(k) for k in z["grad_names"]], z["grad_norms"]))
-    rec = {"norm_ratio": {k: p.grad.double().norm().item() / max(norms[k], 1e-30) for k, p in params.items()},
-           "rel_l2": {k[5:]: _rel_l2(params[k[5:]].grad.cpu().numpy(), z[k]) for k in z.files if k.startswith("grad.")}}
     try:
         out = os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out")
         os.makedirs(out, exist_ok=True)
-        with open(os.path.join(out, "fp32_model_grad_parity.json"), "w") as f:
+        with open(os.path.join(out, name), "w") as f:
             json.dump(rec, f, indent=1, sort_keys=True)
     except OSError:
         pass
-    bad = {k: v for k, v in rec["norm_ratio"].items() if abs(v - 1.0) > 2e-2}
+
+
+def test_whole_model_224_fp32_gradients_vs_reference():
+    """R50 8x8 at 224 px (the bench geometry), B = 2, fp32 storage, against the FLOAT64 run of the unmodified reference
+    (oracle/make_golden.py::model_case_224): loss within 1e-5; every stored gradient within 1e-2 relative L2 and every
+    parameter's gradient norm within 1e-2.  The reference's own float32 run sits 2.8e-3 (mean) / 7.2e-3 (max) from its
+    float64 run on this network (`f32_rel_l2` in the fixture): float32 cannot do better than that floor, whatever the
+    implementation; measured values go to gpurun_out/fp32_model_grad_parity.json."""
+    from mvfnet_b200 import build_recognizer
+    z, depth, t, sd, img, label = _golden_224()
+    m = build_recognizer(model_cfg(depth, t, 0.0), None, None)
+    m.load_state_dict(sd)
+    m = m.cuda().train()
+    loss = m(img.cuda(), label.cuda())["loss_cls"]
+    loss.backward()
+    assert abs(loss.item() - float(z["train_loss"])) < 1e-5 * abs(float(z["train_loss"]))
+    params = dict(m.named_parameters())
+    norms = dict(zip([str(k) for k in z["grad_names"]], z["grad_norms"]))
+    rec = {"norm_ratio": {k: p.grad.double().norm().item() / max(norms[k], 1e-30) for k, p in params.items()},
+           "rel_l2": {k[5:]: _rel_l2(params[k[5:]].grad.cpu().numpy(), z[k]) for k in z.files if k.startswith("grad.")},
+           "reference_f32_floor": {"mean": float(z["f32_rel_l2"].mean()), "max": float(z["f32_rel_l2"].max())}}
+    _record("fp32_model_grad_parity.json", rec)
+    bad = {k: v for k, v in rec["norm_ratio"].items() if abs(v - 1.0) > 1e-2}
     assert not bad, sorted(bad.items(), key=lambda kv: -abs(kv[1] - 1))[:5]
     worst = sorted(rec["rel_l2"].items(), key=lambda kv: -kv[1])[:5]
-    assert worst[0][1] < 2e-2, worst
+    assert worst[0][1] < 1e-2, worst
+
+
+def _reference_autocast_grads(depth, t, sd, img, label):
+    """Gradients of the UNMODIFIED reference model (baseline/_ref) under torch.autocast(bfloat16) on this GPU: the bf16
+    semantics of the reference itself, and the yardstick for how far bf16 storage moves this network's gradients."""
+    import contextlib
+    import io
+    import os
+    import sys
+    root = os.path.join(os.path.dirname(GOLDEN), "..", "baseline", "_ref")
+    if not os.path.isdir(os.path.join(root, "MVFNet", "codes")):
+        return None
+    sys.path[:0] = [os.path.join(root, "mmcv_stub"), os.path.join(root, "MVFNet")]
+    with contextlib.redirect_stdout(io.StringIO()):
+        from codes.models import build_recognizer as ref_build
+        ref = ref_build(model_cfg(depth, t, 0.0), None, None)
+    ref.load_state_dict(sd)
+    ref = ref.cuda().train()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        loss = ref(img.cuda(), label.cuda())["loss_cls"]
+    loss.backward()
+    return loss.item(), {k: p.grad.detach().float().cpu().numpy() for k, p in ref.named_parameters()}
 
 
 def test_whole_model_224_bf16_fused_gradients_vs_reference():
-    """The SAME golden through the production configuration (bf16 autocast, channels_last: every convolution, BatchNorm,
-    MVF module, the stem and the max-pool on this library's kernels).  bf16 storage of ~160 activations / gradients in
-    sequence: each parameter's gradient must agree with the fp32 reference within 5e-2 relative L2 (1e-2 per rounding
-    compounding over the depth of the network; measured values are written to gpurun_out/ for the record), its norm
-    within 5e-2, the loss within 1e-2."""
-    import json
-    import os
+    """The SAME fixture through the production configuration (bf16 autocast, channels_last: every convolution,
+    BatchNorm, MVF module, stem, max-pool, head and loss on this library's kernels).  Whole-network gradients of a
+    random-weight R50 are sensitive: rounding the weights alone to bf16 moves them by ~0.3 relative L2 (fp64 math,
+    measured with the oracle port), so the meaningful statement is comparative -- per parameter,
+        E_ours = relL2(our bf16 gradient, float64 reference)   vs   E_ref = relL2(reference under torch.autocast, float64 reference)
+    on the same GPU: the median of E_ours / E_ref must be <= 1.15 and no parameter may exceed 2x (nor E_ours > 0.6),
+    i.e. this library's bf16 path is as close to the float64 truth as the reference's own bf16 path is.  The loss must
+    agree with the float64 loss within 1e-2.  Measured values go to gpurun_out/bf16_model_grad_parity.json."""
     from mvfnet_b200 import build_recognizer, _lib
     from mvfnet_b200.utils import to_channels_last
-    z, depth, t, seed, img, label = _golden_224()
+    z, depth, t, sd, img, label = _golden_224()
     m = build_recognizer(model_cfg(depth, t, 0.0), None, None)
-    m.load_state_dict(synth_state_dict(seed, depth=depth, n_segment=t))
+    m.load_state_dict(sd)
     m = to_channels_last(m.cuda()).train()
     before = _lib.launch_count()
     with torch.autocast("cuda", dtype=torch.bfloat16):
@@ -164,25 +193,24 @@ def test_whole_model_224_bf16_fused_gradients_vs_reference():
     torch.cuda.synchronize()
     assert _lib.launch_count() - before > 300, "the fused kernels were not used"
     params = dict(m.named_parameters())
-    norms = dict(zip([str(k) for k in z["grad_names"]], z["grad_norms"]))
-    rec = {"loss": loss.item(), "ref_loss": float(z["train_loss"]), "rel_l2": {}, "norm_ratio": {}}
-    for k, p in params.items():
-        rec["norm_ratio"][k] = p.grad.double().norm().item() / max(norms[k], 1e-30)
-    for k in z.files:
-        if k.startswith("grad."):
-            rec["rel_l2"][k[5:]] = _rel_l2(params[k[5:]].grad.float().cpu().numpy(), z[k])
-    out = os.path.join(os.path.dirname(GOLDEN), "..", "gpurun_out")
-    try:
-        os.makedirs(out, exist_ok=True)
-        with open(os.path.join(out, "bf16_model_grad_parity.json"), "w") as f:
-            json.dump(rec, f, indent=1, sort_keys=True)
-    except OSError:
-        pass
-    assert abs(rec["loss"] - rec["ref_loss"]) < 1e-2 * abs(rec["ref_loss"])
-    worst = sorted(rec["rel_l2"].items(), key=lambda kv: -kv[1])[:5]
-    assert worst[0][1] < 5e-2, worst
-    bad = {k: v for k, v in rec["norm_ratio"].items() if abs(v - 1.0) > 5e-2}
-    assert not bad, sorted(bad.items(), key=lambda kv: -abs(kv[1] - 1))[:5]
+    ref = _reference_autocast_grads(depth, t, sd, img, label)
+    if ref is None:
+        pytest.skip("baseline/_ref (the unmodified reference) is not installed next to the tests")
+    ref_loss, ref_grads = ref
+    keys = [k[5:] for k in z.files if k.startswith("grad.")]
+    rec = {"loss": loss.item(), "loss_f64": float(z["train_loss"]), "loss_reference_autocast": ref_loss, "E_ours": {}, "E_ref": {}}
+    for k in keys:
+        rec["E_ours"][k] = _rel_l2(params[k].grad.float().cpu().numpy(), z["grad." + k])
+        rec["E_ref"][k] = _rel_l2(ref_grads[k], z["grad." + k])
+    ratios = {k: rec["E_ours"][k] / max(rec["E_ref"][k], 1e-12) for k in keys}
+    rec["ratio_median"] = float(np.median(list(ratios.values())))
+    rec["ratio_max"] = float(max(ratios.values()))
+    _record("bf16_model_grad_parity.json", rec)
+    assert abs(rec["loss"] - rec["loss_f64"]) < 1e-2 * abs(rec["loss_f64"])
+    assert rec["ratio_median"] <= 1.15, rec["ratio_median"]
+    worst = sorted(ratios.items(), key=lambda kv: -kv[1])[:5]
+    assert worst[0][1] <= 2.0, worst
+    assert max(rec["E_ours"].values()) < 0.6, sorted(rec["E_ours"].items(), key=lambda kv: -kv[1])[:5]
 
 
 def test_whole_model_bf16_channels_last_runs():
