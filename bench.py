@@ -270,6 +270,124 @@ def gpu_bar(dev, world, rank, batches, steps=6, warmup=4):
     return out
 
 
+# --------------------------------------------------------------------------------------- the other BASELINE.json configs
+def light_train_config(dev, world, rank, depth, t, B, steps=6, warmup=3):
+    """configs[2] (R50 16x4) / configs[3] (R101 8x8): the same training step as the headline (uint8 frames, bf16,
+    forward + backward + all-reduce + clip + SGD), a few steps, resident inputs -> whole-job clips/s."""
+    import gc
+    import torch
+    import torch.distributed as dist
+    from mvfnet_b200 import build_recognizer
+    from mvfnet_b200.tail import FlatSGD, preprocess_frames
+    from mvfnet_b200.utils import to_channels_last
+    torch.manual_seed(0)
+    model = to_channels_last(build_recognizer(model_cfg(depth, t), None, None).to(dev)).train()
+    if world > 1:
+        for v in model.state_dict().values():
+            dist.broadcast(v, 0)
+    opt = FlatSGD(model.parameters(), lr=0.015, momentum=0.9, weight_decay=1e-4, nesterov=True, max_norm=40)
+    g = torch.Generator().manual_seed(4000 + rank)
+    img = torch.randint(0, 256, (B, t, PX, PX, 3), generator=g, dtype=torch.uint8).to(dev)
+    lbl = torch.randint(0, 400, (B, 1), generator=g).to(dev)
+
+    def step():
+        opt.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            loss = model(preprocess_frames(img), lbl)["loss_cls"]
+        loss.backward()
+        opt.step(world)
+
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms = float(tt.item())
+    n_params = sum(p.numel() for p in model.parameters())
+    del model, opt, img, lbl
+    gc.collect()
+    torch.cuda.empty_cache()
+    return {"value": world * B * steps / (ms / 1e3), "unit": "clips/s", "ms_per_step": ms / steps, "clips_per_gpu": B,
+            "steps": steps, "allreduce_mb": round(n_params * 4 / 1e6, 1) if world > 1 else 0.0}
+
+
+def inference_config(dev, world, rank, videos=12, px=256, clips=30):
+    """configs[4]: R50 8x8, 256 x 256, 3 crops x 10 clips per video, fcn_testing, eval-mode BatchNorm (test_recognizer.py:72-77,
+    recognizer2d.py:151-179, tsn_clshead.py:99-117): one video (30 clips = 240 frames) per rank per step, no collective.
+    `graph`: the captured CUDA graph of the eval network (mvfnet_b200/infer.py); `eager`: the same kernels launched from
+    Python; `e2e`: uint8 frames from pinned host memory + the (1, 400) scores read back, per video.  videos/s is the
+    whole job (all ranks)."""
+    import gc
+    import torch
+    import torch.distributed as dist
+    from mvfnet_b200 import build_recognizer, _lib
+    from mvfnet_b200.infer import GraphedInference
+    from mvfnet_b200.utils import to_channels_last
+    cfg = model_cfg(50, 8, dropout=0.5)
+    cfg["fcn_testing"] = True
+    cfg["cls_head"]["fcn_testing"] = True
+    torch.manual_seed(0)
+    model = to_channels_last(build_recognizer(cfg, None, dict(average_clips="prob")).to(dev)).eval()
+    g = torch.Generator(device=dev).manual_seed(7)
+    with torch.no_grad():                                            # non-trivial running statistics (they fold into the GEMMs)
+        for m_ in model.modules():
+            if isinstance(m_, torch.nn.modules.batchnorm._BatchNorm):
+                m_.running_mean.normal_(0, 0.1, generator=g)
+                m_.running_var.uniform_(0.5, 1.5, generator=g)
+    gh = torch.Generator().manual_seed(6000 + rank)
+    host = [torch.randint(0, 256, (1, clips * 8, px, px, 3), generator=gh, dtype=torch.uint8).pin_memory() for _ in range(2)]
+    devv = [h.to(dev) for h in host]
+    eng = GraphedInference(model, devv[0], uint8_input=True)
+
+    def timed(fn, n):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms
+
+    l0 = _lib.launch_count()
+    eng(devv[0])
+    launches = _lib.launch_count() - l0                               # a replay launches nothing from the host ...
+    ms_graph = timed(lambda i: eng(devv[i % 2]), videos)
+    ms_eager = timed(lambda i: eng._forward(devv[i % 2]), max(3, videos // 3)) / max(3, videos // 3) * videos
+    ms_e2e = timed(lambda i: eng(host[i % 2]).float().cpu(), videos)
+    out = {"workload": "MVFNet-R50 8x8 %dx%d, %d clips (%d frames) per video, fcn_testing, eval BatchNorm folded into the "
+                       "convolution epilogues, uint8 frames normalised on the GPU" % (px, px, clips, clips * 8),
+           "videos_per_s": world * videos / (ms_graph / 1e3), "clips_per_s": world * videos * clips / (ms_graph / 1e3),
+           "ms_per_video": ms_graph / videos, "eager_videos_per_s": world * videos / (ms_eager / 1e3),
+           "e2e_videos_per_s": world * videos / (ms_e2e / 1e3), "h2d_bytes_per_video": host[0].numel(),
+           "d2h_bytes_per_video": 1600, "kernels_in_graph": "see profiles/", "videos_timed": videos}
+    del eng, model, devv, host
+    gc.collect()
+    torch.cuda.empty_cache()
+    return out
+
+
 # --------------------------------------------------------------------------------------- our arm
 def run_ours(args):
     import torch
@@ -425,13 +543,20 @@ def run_ours(args):
         sweep["B%d" % b] = world * b * n / (timed(dimg, dlbl, n) / 1e3)
         del himg, hlbl, dimg, dlbl
 
+    import gc
+    del model, opt
+    gc.collect()
+    torch.cuda.empty_cache()
+    # ---- BASELINE.json configs[2..4], driver-visible beside the headline: short runs of the same code paths
+    others = None
+    if not args.no_other_configs and (DEPTH, T_FRAMES) == (50, 8):
+        others = {"R50_16x4_train (configs[2])": light_train_config(dev, world, rank, 50, 16, 64),
+                  "R101_8x8_train (configs[3])": light_train_config(dev, world, rank, 101, 8, 80),
+                  "R50_8x8_256px_fcn_test (configs[4])": inference_config(dev, world, rank)}
+
     # ---- the GPU bar: the unmodified reference on PyTorch / cuDNN on the same GPU(s), same run
     bar = None
     if not args.no_gpu_bar:
-        import gc
-        del model, opt
-        gc.collect()
-        torch.cuda.empty_cache()
         bar = gpu_bar(dev, world, rank, [12, 64] + ([B] if B not in (12, 64) else []))
         if "B%d" % B in bar and bar.get("B%d" % B):
             bar["ratio_equal_B"] = value / bar["B%d" % B]
@@ -504,6 +629,8 @@ def run_ours(args):
             "sweep": sweep}
     if bar is not None:
         line["gpu_bar"] = bar
+    if others is not None:
+        line["other_configs"] = others
     if (DEPTH, T_FRAMES) == (50, 8):
         # per-layer max(tensor time, min HBM traffic time) bound of the conv stack, fwd+bwd
         bound = 4680.0 * world
@@ -529,6 +656,7 @@ def main():
     ap.add_argument("--input", default="u8", choices=["u8", "f32"],
                     help="u8: decoded uint8 frames, normalised on the GPU; f32: the reference's float32 wire format")
     ap.add_argument("--sweep", default="12,64", help="extra clips-per-GPU sizes our arm is also timed at (resident inputs)")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of BASELINE.json configs[2..4]")
     ap.add_argument("--no-gpu-bar", action="store_true", help="skip the reference-on-PyTorch/cuDNN arm (gpu_bar)")
     ap.add_argument("--kernels-only", action="store_true",
                     help="profiling runs (ncu): skip the e2e loop and the cpu_baseline sample")

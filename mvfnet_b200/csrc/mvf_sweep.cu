@@ -76,10 +76,12 @@ struct SwArgs {
   const float *wt, *wh, *ww, *gamma, *beta;
   float *running_mean, *running_var, *save_mean, *save_rstd;
   uint2* partials;        // [grid][2*Cg] {fp32 partial sum, epoch}
-  unsigned int* epochs;   // [ngroups] device-resident launch tags, one per channel group: every CTA of the group reads
-                          // the word, tags its partials with it, and the group's first CTA increments it once the
-                          // exchange has completed.  The tag therefore changes from launch to launch without any host
-                          // state: a CUDA-graph replay of the launch is as safe as the launch itself.
+  unsigned int epoch_hi;  // host side: unique per launch CALL (24 bits) -- distinguishes this launch's partials from
+                          // anything an earlier call (any geometry, any workspace reuse) left in the workspace
+  unsigned int* epochs;   // [ngroups] device-resident replay counters (low 8 bits of the tag), one per channel group:
+                          // every CTA of the group reads the word, and the group's first CTA advances it once the
+                          // exchange has completed -- so REPLAYS of one captured launch (same epoch_hi, same
+                          // workspace) carry different tags too.  tag = epoch_hi << 8 | counter.
   int pre_frames;         // sweep-1 frames requested before the grid exchange has completed
   __nv_bfloat16* y;
   long long y_pix;
@@ -189,9 +191,9 @@ mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
   const int nclips = p < g.N ? (g.N - p + g.P - 1) / g.P : 0;
   const int KK = MODE == MODE_TRAIN ? 2 * nclips : nclips;     // clips in this CTA's stream (both sweeps)
   unsigned int epoch = 0;                                      // train mode: this launch's tag (requested first of all)
-  // tag = word + 1, and the word is set to the tag when the exchange is over: whatever the workspace held before
-  // (zero-filled fresh memory, the rows of an earlier launch, whose tags equal the word), no stale row carries it
-  if (MODE == MODE_TRAIN) epoch = __ldcv(a.epochs + cg) + 1u;
+  // low byte = counter + 1 (the counter is set to it when the exchange is over), high bits = the host's call number:
+  // no row left behind by an earlier call or an earlier replay of this call carries the tag
+  if (MODE == MODE_TRAIN) epoch = (a.epoch_hi << 8) | ((__ldcv(a.epochs + cg) + 1u) & 0xffu);
 
   uint64_t* full = reinterpret_cast<uint64_t*>(smem);          // [kRing]
   uint64_t* empty = full + kRing;                               // [kRing]
@@ -570,7 +572,7 @@ mvf_sweep_kernel(const __grid_constant__ CUtensorMap tmx, const SwArgs a) {
       }
       // every CTA of this channel group has published with `epoch`, i.e. has read the word: the next launch (or the
       // next replay of a captured graph) gets a different tag
-      if (rest == 0 && tid == 0) a.epochs[cg] = epoch;
+      if (rest == 0 && tid == 0) a.epochs[cg] = epoch & 0xffu;
       if (tid == 0) mbar_arrive(gate);                            // the producer may now request the rest of sweep 1
       consumer_bar_sync(nconsumer);
       load_affine();
@@ -672,6 +674,14 @@ bool choose_sweep(const mvfb_mvf_desc* d, SwGeo& g) {
   return false;
 }
 
+// Call number of a train-mode launch (24 bits used): tags its partial sums so that words left in the workspace by any
+// earlier call -- another geometry whose rows overlap this one's, recycled allocator blocks, uninitialised memory
+// (probability 2^-32 per word) -- are never mistaken for this launch's.
+unsigned int next_epoch() {
+  static std::atomic<unsigned int> e{0x5eed01u};
+  return e.fetch_add(1u, std::memory_order_relaxed) & 0xffffffu;
+}
+
 template <int MODE, int TT, bool RP>
 int launch_mode(const CUtensorMap& tmx, SwArgs& a, cudaStream_t st) {
   static DevOnce once;
@@ -683,6 +693,7 @@ int launch_mode(const CUtensorMap& tmx, SwArgs& a, cudaStream_t st) {
   const dim3 grid(g.ngroups * g.hsplit * g.wsplit * g.P), block(32 * (g.cwarps + 1));
   const size_t smem = sweep_smem(g);
   if (MODE == MODE_TRAIN) {
+    a.epoch_hi = next_epoch();
     void* params[2] = {(void*)&tmx, (void*)&a};
     // cooperative launch: the driver guarantees that all CTAs are resident, which the grid exchange relies on
     cudaError_t e = cudaLaunchCooperativeKernel((const void*)mvf_sweep_kernel<MODE, TT, RP>, grid, block, params, smem, st);
@@ -756,6 +767,7 @@ int mvf_sweep_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_st
   a.gamma = gamma; a.beta = beta; a.running_mean = rm; a.running_var = rv;
   a.save_mean = save_mean; a.save_rstd = save_rstd;
   a.partials = (uint2*)ws;
+  a.epoch_hi = 0;
   a.epochs = reinterpret_cast<unsigned int*>((char*)ws + sweep_partial_bytes(g));
   a.pre_frames = 4;   // measured best of 1..16; must be >= 1: the last step of sweep 0 reads the first frame of sweep 1
   a.y = (__nv_bfloat16*)y; a.y_pix = y_stride;

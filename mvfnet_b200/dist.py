@@ -68,6 +68,8 @@ class FlatGrads:
 
     def zero_(self):
         """Replaces optimizer.zero_grad(): no kernel at all."""
+        from . import ops
+        ops.new_backward_pass()
         for p in self.params:
             p.grad = None
 

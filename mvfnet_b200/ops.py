@@ -63,6 +63,10 @@ def _L():
         L.bn_bwd.restype = C.c_int
         L.bn_bwd.argtypes = [C.POINTER(BnDesc), _VP, _LL, _VP, _LL, _VP, _LL, _VP, _VP, _VP, _VP, _LL, _VP, _LL, _VP,
                              _VP, _VP, _VP, _VP]
+        L.conv1x1_gemm_bnact.restype = C.c_int
+        L.conv1x1_gemm_bnact.argtypes = [C.POINTER(GemmDesc), _VP, _VP, _VP, _VP, _VP, _VP, _LL, C.c_int, _VP, _VP]
+        L.conv3x3_gemm_bnact.restype = C.c_int
+        L.conv3x3_gemm_bnact.argtypes = [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, C.c_int, _VP, _VP]
         L.conv1x1_gemm_add.restype = C.c_int
         L.conv1x1_gemm_add.argtypes = [C.POINTER(GemmDesc), _VP, _VP, _VP, _VP, _LL, _VP, _VP]
         L.stem_im2col.restype = C.c_int
@@ -96,6 +100,42 @@ _WFORMS = {}
 _WEIGHT_EPOCH = 0
 # id(param) -> (weak reference, bf16 view of the parameter kept current by FlatSGD's update kernel)
 _BF16_SOURCES = {}
+
+
+# id(param) -> (weak reference, fp32 view of the parameter's slice of FlatSGD's flat gradient buffer, with the parameter's
+# own strides): the weight-gradient kernels write there directly and the view is what autograd receives, so nothing is
+# copied when the step packs the gradients (the slice already holds them).
+_GRAD_SINKS = {}
+_SINK_STEP = 0            # bumped by FlatGrads.zero_(): a sink is written at most once per backward (a weight used twice
+                          # in one graph gets an ordinary temporary for its second gradient, which autograd accumulates)
+
+
+def register_grad_sinks(params, views):
+    for p, v in zip(params, views):
+        _GRAD_SINKS[id(p)] = [weakref.ref(p), v, -1]
+
+
+def new_backward_pass():
+    global _SINK_STEP
+    _SINK_STEP += 1
+
+
+def _grad_sink(weight, rows_cols=None):
+    """The flat-buffer slice to write `weight`'s gradient into, or None.  `rows_cols`: require that the slice, read in
+    memory order, is the (rows, cols) row-major matrix the kernel produces."""
+    hit = _GRAD_SINKS.get(id(weight))
+    if hit is None or hit[0]() is not weight or hit[1].device != weight.device:
+        return None
+    v = hit[1]
+    if rows_cols is not None:
+        if weight.dim() == 4 and weight.shape[2] * weight.shape[3] > 1 and not weight.is_contiguous(memory_format=torch.channels_last):
+            return None                                        # the kernels emit (Cout, kh, kw, Cin): channels_last only
+        if v.numel() != rows_cols[0] * rows_cols[1]:
+            return None
+    if hit[2] == _SINK_STEP:
+        return None
+    hit[2] = _SINK_STEP
+    return v
 
 
 def bump_weight_epoch():
@@ -147,6 +187,8 @@ def _wform(weight, form):
         t[:w.shape[0]] = w
     elif form == "fcpadT":
         t = _wform(weight, "fcpad").t().contiguous()
+    elif form == "stem":
+        t = _stem_weight_matrix(weight)
     else:
         raise KeyError(form)
     if len(_WFORMS) > 4096:                                    # models that came and went (test suites)
@@ -204,6 +246,101 @@ def gemm_tn(a1, b, a0=None, k0=0, stats=False, out=None, add=None):
     return out, colsum, colsq
 
 
+# ------------------------------------------------------------------------------------------------ inference (eval BN folded)
+_BNFOLD = {}
+
+
+def bn_fold(bn):
+    """(scale, shift) fp32 of an eval-mode BatchNorm2d: y = x * scale + shift with scale = gamma / sqrt(running_var + eps),
+    shift = beta - running_mean * scale; cached per version of the four tensors."""
+    ver = (bn.weight._version, bn.bias._version, bn.running_mean._version, bn.running_var._version, _WEIGHT_EPOCH)
+    hit = _BNFOLD.get(id(bn))
+    if hit is not None and hit[0]() is bn and hit[1] == ver and hit[2].device == bn.weight.device:
+        return hit[2], hit[3]
+    with torch.no_grad():
+        scale = (bn.weight.float() * torch.rsqrt(bn.running_var.float() + bn.eps)).contiguous()
+        shift = (bn.bias.float() - bn.running_mean.float() * scale).contiguous()
+    _BNFOLD[id(bn)] = (weakref.ref(bn), ver, scale, shift)
+    return scale, shift
+
+
+def bn_infer_ok(*bns):
+    """Eval-mode BatchNorm2d with running statistics whose channel count the GEMM epilogue takes."""
+    return (enabled() and bn_enabled() and not torch.is_grad_enabled()
+            and all(type(b) is torch.nn.BatchNorm2d and not b.training and b.track_running_stats and b.affine
+                    and b.num_features % 64 == 0 for b in bns))
+
+
+def infer_eligible(x, *bns):
+    """Inference fast path: no autograd, bf16 channels_last activations, every BatchNorm in eval mode with running
+    statistics -- the convolution's epilogue applies it (conv1x1_gemm_bnact / conv3x3_gemm_bnact)."""
+    return (x.is_cuda and x.dtype == torch.bfloat16 and x.dim() == 4
+            and x.is_contiguous(memory_format=torch.channels_last) and bn_infer_ok(*bns))
+
+
+def gemm_bnact(a1, b, scale, shift, relu, res=None, a0=None, k0=0):
+    """out = [relu]((A b^T) * scale + shift [+ res]) -- A = [a0[:, :k0] | a1[:, k0:]]; bf16 2-D operands."""
+    L = _L()
+    m, k = a1.shape
+    n = b.shape[0]
+    out = torch.empty((m, n), dtype=torch.bfloat16, device=a1.device)
+    d = GemmDesc()
+    d.M, d.N, d.K, d.K0 = m, n, k, k0
+    d.lda1, d.ldb, d.ldd = a1.stride(0), b.stride(0), n
+    d.lda0 = a0.stride(0) if a0 is not None else 0
+    with _T("gemm1x1", nbytes=2 * (m * k + m * n + n * k + (m * n if res is not None else 0)), flops=2 * m * n * k):
+        rc = L.conv1x1_gemm_bnact(C.byref(d), ptr(a0), ptr(a1), ptr(b), ptr(scale), ptr(shift), ptr(res),
+                                  res.stride(0) if res is not None else 0, int(relu), ptr(out), _stream())
+    _lib.check(rc, "conv1x1_gemm_bnact")
+    return out
+
+
+def conv1x1_bnact(x, weight, bn, relu, residual=None, slab=None, k0=0):
+    """Inference: 1x1 stride-1 convolution + eval BatchNorm (+ residual) (+ ReLU) in one kernel.  `slab`: the compact MVF
+    slab that replaces the first k0 input channels (MVF.forward in eval mode)."""
+    f, cin, h, w = x.shape
+    scale, shift = bn_fold(bn)
+    res = _rows(residual) if residual is not None else None
+    out = gemm_bnact(_rows(x), _wform(weight, "rows"), scale, shift, relu, res=res,
+                     a0=_rows(slab) if slab is not None else None, k0=k0)
+    return _nhwc_from_rows(out, f, h, w)
+
+
+def conv_window_bnact(x, weight, bn, stride, relu, residual=None):
+    """Inference: 3x3 / pad 1 (4-D weight) or strided 1x1 (down-sampling) convolution + eval BatchNorm (+ ReLU)."""
+    L = _L()
+    f, cin, h, w = x.shape
+    three = weight.shape[-1] == 3
+    wk = _wform(weight, "krsc" if three else "rows")
+    cout = wk.shape[0]
+    ho, wo = (h - 1) // stride + 1, (w - 1) // stride + 1
+    scale, shift = bn_fold(bn)
+    d = ConvDesc()
+    d.F, d.H, d.W, d.Cin, d.Cout, d.stride, d.ksize = f, h, w, cin, cout, stride, (3 if three else 1)
+    out = torch.empty((f, ho, wo, cout), dtype=torch.bfloat16, device=x.device)
+    taps, mo = (9 if three else 1), f * ho * wo
+    res = residual.permute(0, 2, 3, 1) if residual is not None else None
+    with _T("conv3x3" if three else "gemm1x1", nbytes=2 * (f * h * w * cin // (1 if three else stride * stride) + mo * cout
+                                                           + taps * cin * cout), flops=2 * mo * cout * taps * cin):
+        rc = L.conv3x3_gemm_bnact(C.byref(d), ptr(x), ptr(wk), ptr(scale), ptr(shift), ptr(res), int(relu), ptr(out), _stream())
+    _lib.check(rc, "conv3x3_gemm_bnact")
+    return out.permute(0, 3, 1, 2)
+
+
+def stem_bnact(x, weight, bn):
+    """Inference stem: im2col + GEMM with eval BatchNorm + ReLU in the epilogue (backbones/resnet.py:481-483)."""
+    L = _L()
+    f, _, h, w = x.shape
+    ho, wo = (h - 1) // 2 + 1, (w - 1) // 2 + 1
+    xb = x.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    a = torch.empty((f * ho * wo, STEM_KP), dtype=torch.bfloat16, device=x.device)
+    with _T("stem_im2col", nbytes=2 * (xb.numel() + a.numel())):
+        _lib.check(L.stem_im2col(ptr(xb), ptr(a), f, h, w, _stream()), "stem_im2col")
+    scale, shift = bn_fold(bn)
+    out = gemm_bnact(a, _wform(weight, "stem"), scale, shift, True)
+    return _nhwc_from_rows(out, f, ho, wo)
+
+
 def add_fusion_enabled() -> bool:
     """MVFB_ADDFUSE=1 folds the sum of the two gradients of a Bottleneck's input into the input-gradient GEMM's epilogue
     (conv1x1_gemm_add).  Off by default: measured neutral on B200 (91.0 vs 91.4 ms per step) -- the K = 64 dgrad GEMMs
@@ -216,8 +353,9 @@ def wgrad_enabled() -> bool:
     return os.environ.get("MVFB_WGRAD", "1") != "0"
 
 
-def gemm_wgrad(g2, x1, x0=None, k0=0):
-    """dW[n, k] = sum_m g2[m, n] X[m, k] with X = [x0[:, :k0] | x1[:, k0:]] -> fp32 (N, K).  bf16 row-major inputs."""
+def gemm_wgrad(g2, x1, x0=None, k0=0, out=None):
+    """dW[n, k] = sum_m g2[m, n] X[m, k] with X = [x0[:, :k0] | x1[:, k0:]] -> fp32 (N, K).  bf16 row-major inputs.
+    `out`: fp32 tensor of N*K elements whose memory receives the row-major result (a flat-gradient-buffer slice)."""
     if not wgrad_enabled():
         gt = g2.t()
         if x0 is None:
@@ -226,7 +364,7 @@ def gemm_wgrad(g2, x1, x0=None, k0=0):
     L = _L()
     m, n = g2.shape
     k = x1.shape[1]
-    dw = torch.empty((n, k), dtype=torch.float32, device=g2.device)
+    dw = out if out is not None else torch.empty((n, k), dtype=torch.float32, device=g2.device)
     d = GemmDesc()
     d.M, d.N, d.K, d.K0 = m, n, k, k0
     d.lda1, d.ldb, d.ldd = x1.stride(0), g2.stride(0), k
@@ -278,7 +416,9 @@ class _Conv1x1(torch.autograd.Function):
             dx2, _, _ = gemm_tn(g2, _wform(ctx.weight, "rowsT"), add=add)   # dX = dY W (+ dL/d identity)  ==  TN GEMM against W^T
             dx = _nhwc_from_rows(dx2, f, h, w)
         if ctx.needs_input_grad[1]:
-            dw = gemm_wgrad(g2, _rows(x)).view(wb.shape[0], cin, 1, 1)
+            sink = _grad_sink(ctx.weight, (wb.shape[0], cin))
+            dw = gemm_wgrad(g2, _rows(x), out=sink)
+            dw = sink if sink is not None else dw.view(wb.shape[0], cin, 1, 1)
         return dx, dw, None, None
 
 
@@ -322,7 +462,9 @@ class _MVFConv1x1(torch.autograd.Function):
         dxp, _, _ = gemm_tn(g2, _wform(ctx.weight, "rowsT"))
         dw = None
         if ctx.needs_input_grad[1]:
-            dw = gemm_wgrad(g2, _rows(xk), x0=_rows(slab), k0=cs).view(wb.shape[0], c, 1, 1)
+            sink = _grad_sink(ctx.weight, (wb.shape[0], c))
+            dw = gemm_wgrad(g2, _rows(xk), x0=_rows(slab), k0=cs, out=sink)
+            dw = sink if sink is not None else dw.view(wb.shape[0], c, 1, 1)
         dx = _nhwc_from_rows(dxp, f, h, w)
         d = _mvf._make_desc(xk, layout, cfg)
         dev = xk.device
@@ -380,13 +522,14 @@ def conv3x3_raw(x, w_krsc, stride, stats=False):
     return out.permute(0, 3, 1, 2), sums
 
 
-def conv3x3_wgrad_raw(g, x, cout, stride, ksize):
-    """dW of the 3x3 (ksize 3 -> (Cout, 3, 3, Cin) fp32) or strided 1x1 (ksize 1 -> (Cout, Cin)) convolution."""
+def conv3x3_wgrad_raw(g, x, cout, stride, ksize, out=None):
+    """dW of the 3x3 (ksize 3 -> (Cout, 3, 3, Cin) fp32) or strided 1x1 (ksize 1 -> (Cout, Cin)) convolution; `out`: fp32
+    tensor of as many elements whose memory receives it."""
     f, cin, h, w = x.shape
     d = ConvDesc()
     d.F, d.H, d.W, d.Cin, d.Cout, d.stride, d.ksize = f, h, w, cin, cout, stride, ksize
     shape = (cout, 3, 3, cin) if ksize == 3 else (cout, cin)
-    dwk = torch.empty(shape, dtype=torch.float32, device=x.device)
+    dwk = out if out is not None else torch.empty(shape, dtype=torch.float32, device=x.device)
     mo = g.shape[0] * g.shape[2] * g.shape[3]
     taps = ksize * ksize
     with _T("wgrad3x3" if ksize == 3 else "wgrad1x1", nbytes=2 * (mo * cout + f * h * w * cin) + 4 * taps * cin * cout,
@@ -422,7 +565,9 @@ class _Conv3x3(torch.autograd.Function):
         # own 3x3 wgrad where it is within ~1.2x of cuDNN (Cin >= 256: layer3/4); the 9-tap re-read of dY makes it
         # 1.5-3.7x slower on the 56x56 / 28x28 layers (tools/wgrad_probe.py), which stay on the library this round
         if need_dw and wgrad_enabled() and (x.shape[1] >= 256 or os.environ.get("MVFB_WGRAD3X3") == "all"):
-            dw = conv3x3_wgrad_raw(g, x, wb.shape[0], st, 3).permute(0, 3, 1, 2)   # (Cout, Cin, 3, 3) view of KRSC
+            sink = _grad_sink(ctx.weight, (wb.shape[0], 9 * x.shape[1]))
+            dw = conv3x3_wgrad_raw(g, x, wb.shape[0], st, 3, out=sink)
+            dw = sink if sink is not None else dw.permute(0, 3, 1, 2)      # (Cout, Cin, 3, 3) view of KRSC
             need_dw = False
         if need_dx or need_dw:
             wcl = wb.contiguous(memory_format=torch.channels_last)
@@ -464,7 +609,9 @@ class _Conv1x1Strided(torch.autograd.Function):
             dx[:, ::st, ::st, :] = dxc.view(f, g.shape[2], g.shape[3], cin)
             dx = dx.permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
-            dw = conv3x3_wgrad_raw(g, x, wb.shape[0], st, 1).view(wb.shape[0], cin, 1, 1)
+            sink = _grad_sink(ctx.weight, (wb.shape[0], cin))
+            dw = conv3x3_wgrad_raw(g, x, wb.shape[0], st, 1, out=sink)
+            dw = sink if sink is not None else dw.view(wb.shape[0], cin, 1, 1)
         return dx, dw, None, None
 
 
@@ -516,7 +663,7 @@ class _StemConv(torch.autograd.Function):
         a = torch.empty((f * ho * wo, STEM_KP), dtype=torch.bfloat16, device=x.device)
         with _T("stem_im2col", nbytes=2 * (xb.numel() + a.numel())):
             _lib.check(L.stem_im2col(ptr(xb), ptr(a), f, h, w, _stream()), "stem_im2col")
-        out, colsum, _ = gemm_tn(a, _stem_weight_matrix(weight), stats=stats)
+        out, colsum, _ = gemm_tn(a, _wform(weight, "stem"), stats=stats)
         ctx.save_for_backward(a)
         ctx.wdtype = weight.dtype
         y = _nhwc_from_rows(out, f, ho, wo)

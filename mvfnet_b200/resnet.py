@@ -116,8 +116,46 @@ class Bottleneck(nn.Module):
     norm2 = property(lambda self: getattr(self, self.norm2_name))
     norm3 = property(lambda self: getattr(self, self.norm3_name))
 
+    def _infer(self, x):
+        """Inference fast path (model.eval(), no autograd, bf16 channels_last): every BatchNorm, residual add and ReLU
+        is the epilogue of the convolution before it -- three or four kernels per block (+ the MVF kernel), one HBM
+        round trip per activation.  None when the block is not eligible."""
+        from . import ops
+        from .mvf import MVF
+        bns = [self.norm1, self.norm2, self.norm3] + ([self.downsample[1]] if self.downsample is not None else [])
+        c1 = self.conv1.net if isinstance(self.conv1, MVF) else self.conv1
+        convs = [c1, self.conv2, self.conv3] + ([self.downsample[0]] if self.downsample is not None else [])
+        if not ops.infer_eligible(x, *bns) or any(type(c) is not nn.Conv2d or c.bias is not None or c.groups != 1 or
+                                                  c.in_channels % 64 or c.out_channels % 64 for c in convs):
+            return None
+        if x.shape[1] != c1.in_channels or (self.conv2.stride[0] == 2 and (x.shape[2] % 2 or x.shape[3] % 2)):
+            return None
+        if isinstance(self.conv1, MVF) and self.conv1.num_shift_channel:
+            mvf = self.conv1
+            if mvf.num_shift_channel % 64:
+                return None
+            from .mvf import mvf_slab_forward
+            cfg, wt, wh, ww, gamma, beta, rm, rv = mvf._kernel_args()
+            slab, xk, _, _, _ = mvf_slab_forward(x, cfg, wt, wh, ww, gamma, beta, rm, rv, out="slab")
+            out = ops.conv1x1_bnact(xk, c1.weight, self.norm1, True, slab=slab, k0=cfg.Cs)
+        else:
+            out = ops.conv1x1_bnact(x, c1.weight, self.norm1, True)
+        out = ops.conv_window_bnact(out, self.conv2.weight, self.norm2, self.conv2.stride[0], True)
+        identity = x
+        if self.downsample is not None:
+            ds = self.downsample[0]
+            if ds.stride[0] == 1:
+                identity = ops.conv1x1_bnact(x, ds.weight, self.downsample[1], False)
+            else:
+                identity = ops.conv_window_bnact(x, ds.weight, self.downsample[1], ds.stride[0], False)
+        return ops.conv1x1_bnact(out, self.conv3.weight, self.norm3, True, residual=identity)
+
     def forward(self, x):
         """resnet.py:208-244.  `self.conv1` is the MVF wrapper in the stages `mvf_freq` selects."""
+        if not torch.is_grad_enabled() and not self.training:
+            out = self._infer(x)
+            if out is not None:
+                return out
         fuse = x.is_cuda and x.dtype == torch.bfloat16
         identity = x
         fused = _conv1x1_id(self.conv1, x) if fuse else None
@@ -215,6 +253,9 @@ class ResNet(nn.Module):
     def _stem(self, x):
         """conv1 -> norm1 -> relu -> maxpool (resnet.py:481-484); own kernels in the bf16 configuration."""
         from . import ops
+        if ops.stem_eligible(x, self.conv1) and ops.bn_infer_ok(self.norm1):
+            out = ops.stem_bnact(x, self.conv1.weight, self.norm1)
+            return ops.maxpool3x3s2(out) if ops.maxpool_eligible(out, self.maxpool) else self.maxpool(out)
         if ops.stem_eligible(x, self.conv1):
             out, sums = ops.stem_conv(x, self.conv1.weight, True)
         else:

@@ -194,6 +194,8 @@ class FlatSGD:
         self.grads.restride(self.params)
         self.flat_p16.copy_(self.flat_p)
         ops.register_bf16_sources(self.params, self._views16)
+        (views,) = self.grads.views.values()
+        ops.register_grad_sinks(self.params, views)            # weight-gradient kernels write into the flat buffer
         self.steps = 0
 
     def zero_grad(self, set_to_none=True):

@@ -261,3 +261,61 @@ def test_whole_model_bf16_eval_and_fcn_testing():
         assert abs(got[0, top5].sum() - ref[0, top5].sum()) < 0.1
         assert np.abs(got - ref).sum() < 0.5
     assert np.abs(prob - prob_fcn).sum() < 3e-2
+
+
+def test_fcn_testing_256_vs_reference_on_gpu():
+    """BASELINE configs[4] semantics at 256 x 256: the UNMODIFIED reference (baseline/_ref) with fcn_testing=True on model
+    and head, eval-mode BatchNorm, average_clips='prob' (test_recognizer.py:72-77, recognizer2d.py:151-179,
+    tsn_clshead.py:99-117 -- its Conv3d head is created with .cuda(), so this comparison can only run on the GPU box)
+    against (a) our fp32 model, 1e-4, and (b) the production inference path: bf16, eval BatchNorm folded into the
+    convolution epilogues, uint8 frames normalised on the GPU, replayed from a CUDA graph (mvfnet_b200/infer.py)."""
+    import contextlib
+    import io
+    import os
+    import sys
+    from mvfnet_b200 import build_recognizer, _lib
+    from mvfnet_b200.infer import GraphedInference
+    from mvfnet_b200.utils import to_channels_last
+    from mvfnet_b200.tail import IMG_NORM_MEAN, IMG_NORM_STD
+    root = os.path.join(os.path.dirname(GOLDEN), "..", "baseline", "_ref")
+    if not os.path.isdir(os.path.join(root, "MVFNet", "codes")):
+        pytest.skip("baseline/_ref (the unmodified reference) is not installed next to the tests")
+    sys.path[:0] = [os.path.join(root, "mmcv_stub"), os.path.join(root, "MVFNet")]
+    t, clips, px = 8, 3, 256
+    cfg = model_cfg(50, t, 0.5)
+    cfg["fcn_testing"] = True
+    cfg["cls_head"]["fcn_testing"] = True
+    sd = synth_state_dict(11, depth=50, n_segment=t, conditioned=True)
+    with contextlib.redirect_stdout(io.StringIO()):
+        from codes.models import build_recognizer as ref_build
+        ref = ref_build({k: (dict(v) if isinstance(v, dict) else v) for k, v in cfg.items()}, None, dict(average_clips="prob"))
+    ref.load_state_dict(sd)
+    ref = ref.cuda().eval()
+    g = torch.Generator().manual_seed(3)
+    u8 = torch.randint(0, 256, (1, clips * t, px, px, 3), generator=g, dtype=torch.uint8)
+    mean, std = torch.tensor(IMG_NORM_MEAN), torch.tensor(IMG_NORM_STD)
+    img = ((u8.float().flip(-1) - mean) / std).permute(0, 1, 4, 2, 3).contiguous()     # the reference's float32 wire format
+    with torch.no_grad():
+        want = ref(img.cuda(), None, return_loss=False)                                   # (1, 400) numpy
+    assert want.shape == (1, 400) and abs(want.sum() - 1) < 1e-4
+
+    ours = build_recognizer({k: (dict(v) if isinstance(v, dict) else v) for k, v in cfg.items()}, None, dict(average_clips="prob"))
+    ours.load_state_dict(sd)
+    ours = ours.cuda().eval()
+    with torch.no_grad():
+        got32 = ours(img.cuda(), None, return_loss=False)
+    np.testing.assert_allclose(got32, want, rtol=1e-3, atol=1e-6)
+
+    ours = to_channels_last(ours)
+    before = _lib.launch_count()
+    eng = GraphedInference(ours, u8.cuda(), uint8_input=True)
+    assert _lib.launch_count() - before > 150, "the fused inference kernels were not used"
+    for _ in range(2):
+        got = eng(u8.cuda()).float().cpu().numpy()
+    assert got.shape == (1, 400) and abs(got.sum() - 1) < 1e-3
+    assert got.argmax() == want.argmax()
+    assert np.abs(got - want).sum() < 0.1, np.abs(got - want).sum()                     # L1 distance of the distributions
+    top5 = np.argsort(want[0])[-5:]
+    assert abs(got[0, top5].sum() - want[0, top5].sum()) < 0.03
+    eager = eng._forward(u8.cuda()).float().cpu().numpy()
+    np.testing.assert_allclose(got, eager, rtol=0, atol=1e-6)                           # the graph replays what eager computes

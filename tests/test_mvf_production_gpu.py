@@ -218,3 +218,46 @@ def test_train_forward_survives_cuda_graph_replay():
         torch.cuda.synchronize()
         assert torch.equal(mg, eager[i][1]) and torch.equal(rg, eager[i][2]), "batch statistics differ on replay %d" % i
         assert torch.equal(yg, eager[i][0])
+
+
+def test_train_forward_with_recycled_workspace_across_geometries():
+    """The train-mode forward's grid exchange tags its partial sums; rows left in a workspace by EARLIER calls with other
+    geometries (torch's caching allocator hands the same block to consecutive MVF modules of a step) must never be
+    accepted.  One explicit workspace is shared by alternating shapes and clip counts; every result must be bit-identical
+    to the same call on a private, zeroed workspace."""
+    import ctypes as C
+    from mvfnet_b200 import _lib
+    from mvfnet_b200.mvf import _make_desc, ptr, _stream
+    L = _lib.lib()
+    shapes = [(1024, 14, 128, 8, 40), (2048, 7, 256, 8, 40), (512, 28, 64, 8, 24), (1024, 14, 128, 16, 20), (1024, 14, 128, 8, 64)]
+    mods, xs = [], []
+    for i, (Cc, H, Cs, T, N) in enumerate(shapes):
+        m, _, _ = make_module(Cc, Cs, T, True, seed=50 + i)
+        mods.append(m)
+        xs.append(torch.randn((N * T, H, H, Cc), device="cuda").to(torch.bfloat16).permute(0, 3, 1, 2))
+    shared = torch.zeros(4 << 20, dtype=torch.uint8, device="cuda")
+
+    def call(i, ws):
+        m, x = mods[i], xs[i]
+        Cc, H, Cs, T, N = shapes[i]
+        cfg = m._cfg()
+        wt, wh, ww = (w.detach().float().contiguous() for w in m._taps())
+        d = _make_desc(x, _lib.MVFB_NHWC, cfg)
+        assert L.mvf_fwd_workspace_bytes(C.byref(d)) <= ws.numel()
+        y = torch.empty((N * T, H, H, Cs), dtype=torch.bfloat16, device="cuda")
+        mean, rstd = torch.empty(Cs, device="cuda"), torch.empty(Cs, device="cuda")
+        rm, rv = torch.zeros(Cs, device="cuda"), torch.ones(Cs, device="cuda")
+        rc = L.mvf_fwd(C.byref(d), ptr(x), ptr(y), Cs, ptr(wt), ptr(wh), ptr(ww), ptr(m.bn.weight), ptr(m.bn.bias), ptr(rm),
+                       ptr(rv), ptr(mean), ptr(rstd), ptr(ws), ws.numel(), _stream())
+        assert rc == 0, L.mvf_b200_last_error()
+        assert _lib.last_kernel() == "sweep"
+        return y, mean, rstd
+
+    want = [call(i, torch.zeros(4 << 20, dtype=torch.uint8, device="cuda")) for i in range(len(shapes))]
+    order = [0, 1, 0, 2, 3, 0, 4, 1, 2, 4, 0, 3, 1, 0]
+    for rep in range(3):
+        for i in order:
+            y, mean, rstd = call(i, shared)
+            torch.cuda.synchronize()
+            assert torch.equal(mean, want[i][1]) and torch.equal(rstd, want[i][2]), "stale partial sums accepted (shape %d)" % i
+            assert torch.equal(y, want[i][0])
