@@ -132,6 +132,7 @@ const char* mvf_b200_plan(const mvfb_mvf_desc* d, int backward) {
     if (on(MVFB_KERNEL_STREAM) && mvf_stream_supported(d)) return "stream";
     if (on(MVFB_KERNEL_RING) && mvf_fast_supported(d)) return "ring";
   } else {
+    if (on(MVFB_KERNEL_SWEEP) && mvf_sweep_bwd_supported(d)) return "sweep";
     if (on(MVFB_KERNEL_STREAM) && mvf_stream_bwd_supported(d)) return "stream";
     if (on(MVFB_KERNEL_RING) && mvf_fast_bwd_supported(d)) return "ring";
   }
@@ -162,6 +163,8 @@ size_t mvf_bwd_workspace_bytes(const mvfb_mvf_desc* d) {
   size_t fast = mvf_fast_bwd_supported(d) ? head + mvf_fast_ws(d) : 0;
   const size_t stream = mvf_stream_bwd_supported(d) ? head + mvf_stream_bwd_ws(d) : 0;
   if (stream > fast) fast = stream;
+  const size_t sweep = mvf_sweep_bwd_supported(d) ? head + mvf_sweep_bwd_ws(d) : 0;
+  if (sweep > fast) fast = sweep;
   return generic > fast ? generic : fast;
 }
 
@@ -251,6 +254,12 @@ int mvf_bwd(const mvfb_mvf_desc* d, const void* g, long long g_stride, const voi
   }
   ws += 2 * sizeof(float) * (((size_t)d->Cs + 63) / 64 * 64);
   const int force = option(OPT_FORCE_BWD);
+  if ((force == 0 || force == MVFB_KERNEL_SWEEP) && mvf_sweep_bwd_supported(d)) {
+    rc = mvf_sweep_bwd(d, g, g_stride, x, dx, dx_stride, wt, wh, ww, gamma, beta, mean, rstd, dwt, dwh, dww, dgamma,
+                       dbeta, ws, st);
+    if (rc == MVFB_OK) note_kernel("sweep");
+    if (rc != MVFB_ERR_UNSUPPORTED) return rc;
+  }
   if ((force == 0 || force == MVFB_KERNEL_STREAM) && mvf_stream_bwd_supported(d)) {
     rc = mvf_stream_bwd(d, g, g_stride, x, dx, dx_stride, wt, wh, ww, gamma, beta, mean, rstd, dwt, dwh, dww, dgamma,
                         dbeta, ws, st);

@@ -194,32 +194,32 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
-      // optional addend (out = A B^T + res): this thread's row of it, 32 columns (64 contiguous bytes) per chunk; the
-      // first chunk is requested before the accumulator is waited for
-      const long long grow = (long long)mt * BM + row;
-      const uint4* res_row = (a.res && grow < a.M)
-                                 ? reinterpret_cast<const uint4*>(a.res + grow * a.ldr + nt * BN + half * kHalfN) : nullptr;
-      uint4 rq[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-      if (res_row) {
-#pragma unroll
-        for (int q = 0; q < 4; ++q) rq[q] = __ldg(res_row + q);
-      }
-      mbar_wait(&tmem_full[acc], acc_ph);
-      tc_fence_after();
       // staging tile of the previous store must have been read by the TMA engine
       if (et == 0) tma_store_wait_read<0>();
       named_bar_sync(1, kEpiThreads);
+      // optional addend (out = A B^T + res): its 128 x BN tile is copied into the staging buffer FIRST, coalesced (a
+      // warp reads whole 128- .. 512-byte rows), in the swizzled layout the results will have -- while this tile's MMAs
+      // are still running.  Each thread later adds its own row chunks from shared memory (the first version read the
+      // addend row-wise from global memory per thread: 32 cache lines per load instruction, 3.5 ms per step).
+      if (a.res) {
+        constexpr int kChunksPerRow = BN / 8;                    // 16-byte chunks per tile row
+        const long long m0 = (long long)mt * BM;
+#pragma unroll 4
+        for (int idx = et; idx < BM * kChunksPerRow; idx += kEpiThreads) {
+          const int r = idx / kChunksPerRow, ch = idx - r * kChunksPerRow;
+          uint4 v4 = make_uint4(0u, 0u, 0u, 0u);
+          if (m0 + r < a.M) v4 = __ldg(reinterpret_cast<const uint4*>(a.res + (m0 + r) * a.ldr + nt * BN + ch * 8));
+          *reinterpret_cast<uint4*>(staging + (size_t)(ch >> 3) * (BM * 128) + (size_t)r * 128 + (((ch & 7) ^ (r & 7)) << 4)) = v4;
+        }
+      }
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc_fence_after();
+      if (a.res) named_bar_sync(1, kEpiThreads);               // every addend chunk is in place
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BN + half * kHalfN) + ((uint32_t)(lane_grp * 32) << 16);
 #pragma unroll 1
       for (int cc = 0; cc < kHalfN; cc += 32) {
         const int c0 = half * kHalfN + cc;                     // first column of this chunk within the tile
         uint32_t v[32];
-        // the addend of the NEXT 32 columns is requested now, a whole chunk ahead of its use
-        uint4 rn[4] = {make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0), make_uint4(0, 0, 0, 0)};
-        if (res_row && cc + 32 < kHalfN) {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) rn[q] = __ldg(res_row + (cc + 32) / 8 + q);
-        }
         tmem_ld_32x32b_x32(taddr + cc, v);
         tmem_ld_wait();
         if (a.ep_scale) {                                      // every lane reads the same 32 floats: L1 broadcast
@@ -234,26 +234,25 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
             v[4 * q + 3] = __float_as_uint(fmaf(__uint_as_float(v[4 * q + 3]), s4.w, h4.w));
           }
         }
-        if (res_row) {
+        uint8_t* panel = staging + (size_t)(c0 >> 6) * (BM * 128) + (size_t)row * 128;
+        const int chunk0 = (c0 & 63) >> 3;
+        if (a.res) {                                           // this thread's own row chunks of the staged addend
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint32_t w4[4] = {rq[q].x, rq[q].y, rq[q].z, rq[q].w};
+            const uint4 r4 = *reinterpret_cast<const uint4*>(panel + (((chunk0 + q) ^ (row & 7)) << 4));
+            const uint32_t w4[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               v[q * 8 + 2 * e] = __float_as_uint(__uint_as_float(v[q * 8 + 2 * e]) + bf16_lo(w4[e]));
               v[q * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(v[q * 8 + 2 * e + 1]) + bf16_hi(w4[e]));
             }
           }
-#pragma unroll
-          for (int q = 0; q < 4; ++q) rq[q] = rn[q];
         }
         if (a.ep_relu) {
 #pragma unroll
           for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(fmaxf(__uint_as_float(v[q]), 0.f));
         }
         // 32 fp32 -> 32 bf16 = 64 B = four 16-byte chunks of this row in panel c0/64
-        uint8_t* panel = staging + (size_t)(c0 >> 6) * (BM * 128) + (size_t)row * 128;
-        const int chunk0 = (c0 & 63) >> 3;
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           uint4 o;

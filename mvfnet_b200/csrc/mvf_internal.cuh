@@ -55,6 +55,15 @@ int mvf_stream_bwd(const mvfb_mvf_desc* d, const void* g, long long g_stride, co
                    const float* beta, const float* mean, const float* rstd, float* dwt, float* dwh, float* dww,
                    float* dgamma, float* dbeta, void* ws, cudaStream_t st);
 
+// ---- mvf_sweep_bwd.cu : bf16 NHWC backward, FHFMA arithmetic, statistics sweep + dx sweep in one cooperative launch
+//      (preferred backward path: whole-frame tiles, 4-channel items, 1 / 2 / 4 items per thread)
+bool mvf_sweep_bwd_supported(const mvfb_mvf_desc* d);
+size_t mvf_sweep_bwd_ws(const mvfb_mvf_desc* d);
+int mvf_sweep_bwd(const mvfb_mvf_desc* d, const void* g, long long g_stride, const void* x, void* dx,
+                  long long dx_stride, const float* wt, const float* wh, const float* ww, const float* gamma,
+                  const float* beta, const float* mean, const float* rstd, float* dwt, float* dwh, float* dww,
+                  float* dgamma, float* dbeta, void* ws, cudaStream_t st);
+
 // sums (fp64, [11][Cs]) -> fp32 parameter gradients (mvf_generic.cu)
 __global__ void mvf_bwd_finalize(const double* sums, int Cs, int h_shares, int w_shares, int has_h, int has_w,
                                  int use_hs, float* dwt, float* dwh, float* dww, float* dgamma, float* dbeta);

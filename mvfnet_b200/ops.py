@@ -342,10 +342,11 @@ def stem_bnact(x, weight, bn):
 
 
 def add_fusion_enabled() -> bool:
-    """MVFB_ADDFUSE=1 folds the sum of the two gradients of a Bottleneck's input into the input-gradient GEMM's epilogue
-    (conv1x1_gemm_add).  Off by default: measured neutral on B200 (91.0 vs 91.4 ms per step) -- the K = 64 dgrad GEMMs
-    of layer1 are epilogue-bound and pay for the addend's row-wise reads what autograd's coalesced add kernel cost."""
-    return os.environ.get("MVFB_ADDFUSE", "0") == "1"
+    """The two gradients of a Bottleneck's input (through conv1 and through the identity path, backbones/resnet.py:211-213,
+    238) are summed in the epilogue of conv1's input-gradient GEMM (conv1x1_gemm_add: the addend tile is staged through
+    shared memory, coalesced, while the tile's MMAs run) instead of by an autograd add kernel that streams three full
+    tensors.  MVFB_ADDFUSE=0 switches it off (A/B measurements only)."""
+    return os.environ.get("MVFB_ADDFUSE", "1") != "0"
 
 
 def wgrad_enabled() -> bool:

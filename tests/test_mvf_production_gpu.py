@@ -1,7 +1,7 @@
 """MVF parity at PRODUCTION clip counts: the dispatch the headline bench actually runs.
 
-`mvf_sweep_kernel` (forward) and the backward stream / sweep kernels deal clips round-robin over P = SMs / lanes CTAs
-(P = 37 for the 14x14x128 slab, 74 for 28x28x64, 18 for 7x7x256), so only N > P exercises what a training step at
+`mvf_sweep_kernel` (forward) and `mvf_sweep_bwd_kernel` (backward) deal clips round-robin over P = SMs / lanes CTAs
+(P = 18 for the 14x14x128 slab forward and backward, 9 / 18 for 28x28x64, 18 / 37 for 7x7x256), so only N > P exercises what a training step at
 B = 148..160 clips does: several clips per CTA with an uneven deal, ring-slot reuse by the producer, the next-clip
 prefetch across a clip boundary, sweep-1 gating, partial sums over several clips (MVF.py:104-138 semantics: the
 temporal taps must never leak from one clip into the next).  Every test asserts WHICH kernel tier served the call
@@ -156,7 +156,7 @@ def test_fallback_tiers_pinned(tier, training):
     x = torch.randn((N * T, H, H, C), generator=gen, device="cuda").to(torch.bfloat16).permute(0, 3, 1, 2)
     gy = torch.randn((N * T, H, H, C), generator=gen, device="cuda").to(torch.bfloat16).permute(0, 3, 1, 2)
     xd = x.detach().requires_grad_(True)
-    with _lib.force_kernel(fwd=tier, bwd=tier):
+    with _lib.force_kernel(fwd=tier, bwd=tier if tier != "sweep" else "sweep"):
         y = m(xd)
         assert _lib.last_kernel() == tier
         y.backward(gy)
