@@ -80,7 +80,13 @@ typedef struct {
  * tells what actually ran. */
 const char* mvf_b200_plan(const mvfb_mvf_desc* d, int backward);
 
-/* Bytes of scratch `workspace` the forward / backward need for this descriptor. */
+/* Bytes of scratch `workspace` the forward / backward need for this descriptor.  Its contents on entry are arbitrary
+ * (uninitialised, zeroed, or left behind by any earlier call with any descriptor): the train-mode forward and the
+ * backward exchange per-CTA partial sums through it as {value, tag} words whose tag is unique per call (a host call
+ * number) and per replay of a captured call (a counter the kernel keeps IN the workspace) -- so the calls are safe to
+ * capture in a CUDA graph and to replay, provided each captured call keeps its own workspace, and two calls that may run
+ * concurrently must not share one.  Both are cooperative launches (one CTA per SM at most, all resident); if the device
+ * cannot co-schedule the grid the call steps down to the two-launch kernels. */
 size_t mvf_fwd_workspace_bytes(const mvfb_mvf_desc* d);
 size_t mvf_bwd_workspace_bytes(const mvfb_mvf_desc* d);
 
@@ -107,8 +113,7 @@ int mvf_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_stride, 
  * Outputs dwt/dwh/dww (Cs,3) fp32, dgamma/dbeta (Cs) fp32 are OVERWRITTEN.  With share (wh==wt and/or
  * ww==wt) the views' tap gradients are summed into dwt and dwh/dww may be NULL.
  * training: save_mean/save_rstd from the forward; eval: running stats.
- * The library owns one 512-byte device allocation per GPU (grid-barrier words of the single-launch train-mode
- * forward, created on first use, never freed); every other buffer is the caller's.
+ * The library owns no device memory: every buffer, the workspace included, is the caller's.
  * dx MAY alias g (same pointer and stride): every kernel reads a frame of g completely before that frame's
  * dx is written -- this is how the caller turns "dL/dx' for all C channels" into dL/dx in place.
  */
@@ -117,6 +122,16 @@ int mvf_bwd(const mvfb_mvf_desc* d, const void* g, long long g_stride, const voi
             const float* running_mean, const float* running_var, const float* save_mean, const float* save_rstd,
             float* dwt, float* dwh, float* dww, float* dgamma, float* dbeta, void* workspace,
             size_t workspace_bytes, mvfb_stream_t stream);
+
+/* mvf_bwd with the gradient of the Bottleneck's identity path folded in: dx (slab channels) = mvf_bwd(...) + dx_add, where
+ * dx_add is addressed like dx (same stride) -- `out += identity` of backbones/resnet.py:238 sends a second gradient to the
+ * block input, and summing it here (and in conv1x1_gemm_add_cols for the other channels) saves autograd's full-tensor add.
+ * Served by the sweep tier only (MVFB_ERR_UNSUPPORTED otherwise: ask mvf_b200_plan first).  dx_add must not alias dx. */
+int mvf_bwd_add(const mvfb_mvf_desc* d, const void* g, long long g_stride, const void* x, void* dx, long long dx_stride,
+                const float* wt, const float* wh, const float* ww, const float* gamma, const float* beta,
+                const float* running_mean, const float* running_var, const float* save_mean, const float* save_rstd,
+                float* dwt, float* dwh, float* dww, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+                const void* dx_add, mvfb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------------
  * 1x1 convolution on NHWC bf16 activations as a tensor-core GEMM  --  replaces nn.Conv2d(kernel_size=1,
@@ -148,6 +163,12 @@ int conv1x1_gemm(const mvfb_gemm_desc* d, const void* a0, const void* a1, const 
  * in one pass instead of a GEMM and a separate full-tensor add (backbones/resnet.py:211-213, 238). */
 int conv1x1_gemm_add(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, const void* res,
                      long long ldr, void* out, mvfb_stream_t stream);
+
+/* conv1x1_gemm_add with the addend applied to columns >= first_col only (a multiple of 32): the input-gradient of an
+ * MVF-wrapped conv1, whose slab columns [0, Cs) still have to pass through mvf_bwd_add before they meet the identity
+ * path's gradient. */
+int conv1x1_gemm_add_cols(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, const void* res,
+                          long long ldr, int first_col, void* out, mvfb_stream_t stream);
 
 /* Inference form of the same layers: an eval-mode BatchNorm2d (+ residual) (+ ReLU) folded into the convolution's epilogue,
  *   out = [relu]( (A B^T)[m, n] * scale[n] + shift[n] [+ res[m*ldr + n]] ),
@@ -293,6 +314,12 @@ int head_ce_bwd(const float* ds, const float* gout, void* dlogits, long long ldl
  *                       A zero-initialised m reproduces torch's first step (buf = grad).
  * ---------------------------------------------------------------------------------------------- */
 int flat_sqnorm(const float* g, long long n, double* out, mvfb_stream_t stream);
+/* All transposed weight forms of a step in one launch: `tiles` is a DEVICE array of `ntiles` records
+ *   struct { const bf16* src; bf16* dst; int lds, ldd, rows, cols, r0, c0; }   (40 bytes, 8-byte aligned)
+ * each naming one 32 x 32 tile at (r0, c0) of a rows x cols bf16 matrix (element (r, c) at src[r*lds + c]) whose transpose
+ * goes to dst[c*ldd + r].  The host builds the table once (the flat weight buffers never move): the W^T operands of the
+ * 1x1 input-gradient GEMMs and the rotated (Cin, 3, 3, Cout) operands of the 3x3 ones (one record set per filter tap). */
+int transpose_tiles(const void* tiles, long long ntiles, mvfb_stream_t stream);
 int sgd_nesterov_step(float* p, float* mom, const float* g, void* p_bf16, long long n, const double* sqnorm,
                       float* norm_out, float grad_scale, float max_norm, float lr, float momentum, float weight_decay,
                       int nesterov, mvfb_stream_t stream);

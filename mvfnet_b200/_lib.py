@@ -44,6 +44,8 @@ def _declare(l):
     l.mvf_bwd.restype = C.c_int
     l.mvf_bwd.argtypes = [C.POINTER(MvfDesc), _VP, _LL, _VP, _VP, _LL, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP, _FP,
                           _FP, _FP, _FP, _FP, _FP, _VP, _SZ, _VP]
+    l.mvf_bwd_add.restype = C.c_int
+    l.mvf_bwd_add.argtypes = l.mvf_bwd.argtypes[:-1] + [_VP, _VP]
     l.mvf_b200_last_kernel.restype = C.c_char_p
     l.mvf_b200_plan.restype = C.c_char_p
     l.mvf_b200_plan.argtypes = [C.POINTER(MvfDesc), C.c_int]

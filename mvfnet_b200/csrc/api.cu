@@ -213,11 +213,11 @@ int mvf_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_stride, 
   return rc;
 }
 
-int mvf_bwd(const mvfb_mvf_desc* d, const void* g, long long g_stride, const void* x, void* dx, long long dx_stride,
+static int mvf_bwd_impl(const mvfb_mvf_desc* d, const void* g, long long g_stride, const void* x, void* dx, long long dx_stride,
             const float* wt, const float* wh, const float* ww, const float* gamma, const float* beta,
             const float* running_mean, const float* running_var, const float* save_mean, const float* save_rstd,
             float* dwt, float* dwh, float* dww, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
-            mvfb_stream_t stream) {
+            const void* dx_add, mvfb_stream_t stream) {
   int rc = check_mvf_desc(d);
   if (rc) return rc;
   MVFB_CHECK(g && x && dx && wt && dwt, MVFB_ERR_ARG, "null g / x / dx / wt / dwt");
@@ -256,10 +256,11 @@ int mvf_bwd(const mvfb_mvf_desc* d, const void* g, long long g_stride, const voi
   const int force = option(OPT_FORCE_BWD);
   if ((force == 0 || force == MVFB_KERNEL_SWEEP) && mvf_sweep_bwd_supported(d)) {
     rc = mvf_sweep_bwd(d, g, g_stride, x, dx, dx_stride, wt, wh, ww, gamma, beta, mean, rstd, dwt, dwh, dww, dgamma,
-                       dbeta, ws, st);
+                       dbeta, ws, dx_add, st);
     if (rc == MVFB_OK) note_kernel("sweep");
     if (rc != MVFB_ERR_UNSUPPORTED) return rc;
   }
+  MVFB_CHECK(dx_add == nullptr, MVFB_ERR_UNSUPPORTED, "mvf_bwd_add is served by the sweep tier only (see mvf_b200_plan)");
   if ((force == 0 || force == MVFB_KERNEL_STREAM) && mvf_stream_bwd_supported(d)) {
     rc = mvf_stream_bwd(d, g, g_stride, x, dx, dx_stride, wt, wh, ww, gamma, beta, mean, rstd, dwt, dwh, dww, dgamma,
                         dbeta, ws, st);
@@ -278,6 +279,25 @@ int mvf_bwd(const mvfb_mvf_desc* d, const void* g, long long g_stride, const voi
                        dbeta, ws, st);
   if (rc == MVFB_OK) note_kernel("generic");
   return rc;
+}
+
+int mvf_bwd(const mvfb_mvf_desc* d, const void* g, long long g_stride, const void* x, void* dx, long long dx_stride,
+            const float* wt, const float* wh, const float* ww, const float* gamma, const float* beta,
+            const float* running_mean, const float* running_var, const float* save_mean, const float* save_rstd,
+            float* dwt, float* dwh, float* dww, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+            mvfb_stream_t stream) {
+  return mvf_bwd_impl(d, g, g_stride, x, dx, dx_stride, wt, wh, ww, gamma, beta, running_mean, running_var, save_mean,
+                      save_rstd, dwt, dwh, dww, dgamma, dbeta, workspace, workspace_bytes, nullptr, stream);
+}
+
+int mvf_bwd_add(const mvfb_mvf_desc* d, const void* g, long long g_stride, const void* x, void* dx, long long dx_stride,
+                const float* wt, const float* wh, const float* ww, const float* gamma, const float* beta,
+                const float* running_mean, const float* running_var, const float* save_mean, const float* save_rstd,
+                float* dwt, float* dwh, float* dww, float* dgamma, float* dbeta, void* workspace, size_t workspace_bytes,
+                const void* dx_add, mvfb_stream_t stream) {
+  MVFB_CHECK(dx_add != nullptr, MVFB_ERR_ARG, "mvf_bwd_add needs the addend");
+  return mvf_bwd_impl(d, g, g_stride, x, dx, dx_stride, wt, wh, ww, gamma, beta, running_mean, running_var, save_mean,
+                      save_rstd, dwt, dwh, dww, dgamma, dbeta, workspace, workspace_bytes, dx_add, stream);
 }
 
 }  // extern "C"

@@ -46,6 +46,7 @@ struct GemmArgs {
   float* colsq;                    // [N] or null
   const __nv_bfloat16* res;        // optional (M, N) bf16 addend, leading dimension ldr: out = A B^T + res
   long long ldr;
+  int res_col0;                    // the addend applies to columns >= res_col0 only (a multiple of 32)
   // inference epilogue (eval-mode BatchNorm folded into the convolution): out = [relu]((A B^T) * ep_scale[n] + ep_shift[n] [+ res])
   const float* ep_scale;           // [N] or null
   const float* ep_shift;           // [N] (with ep_scale)
@@ -236,7 +237,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         }
         uint8_t* panel = staging + (size_t)(c0 >> 6) * (BM * 128) + (size_t)row * 128;
         const int chunk0 = (c0 & 63) >> 3;
-        if (a.res) {                                           // this thread's own row chunks of the staged addend
+        if (a.res && nt * BN + c0 >= a.res_col0) {             // this thread's own row chunks of the staged addend
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint4 r4 = *reinterpret_cast<const uint4*>(panel + (((chunk0 + q) ^ (row & 7)) << 4));
@@ -353,6 +354,7 @@ struct Epi {                       // optional inference epilogue
   const float* scale = nullptr;
   const float* shift = nullptr;
   int relu = 0;
+  int res_col0 = 0;                // first column the addend applies to
 };
 
 template <int BN>
@@ -373,7 +375,7 @@ int launch(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* 
   GemmArgs a;
   a.M = d->M; a.N = d->N; a.K = d->K; a.K0 = d->K0;
   a.colsum = colsum; a.colsq = colsq;
-  a.res = (const __nv_bfloat16*)res; a.ldr = ldr;
+  a.res = (const __nv_bfloat16*)res; a.ldr = ldr; a.res_col0 = ep.res_col0;
   a.ep_scale = ep.scale; a.ep_shift = ep.shift; a.ep_relu = ep.relu;
   a.Cin = a.Ho = a.Wo = a.stride = a.pad = 0;
   a.ks = 1;
@@ -400,7 +402,7 @@ int launch_conv3x3(const mvfb_conv_desc* d, const void* x, const void* w, void* 
   GemmArgs a;
   a.M = M; a.N = d->Cout; a.K = taps * d->Cin; a.K0 = 0;
   a.colsum = colsum; a.colsq = colsq;
-  a.res = (const __nv_bfloat16*)res; a.ldr = d->Cout;
+  a.res = (const __nv_bfloat16*)res; a.ldr = d->Cout; a.res_col0 = 0;
   a.ep_scale = ep.scale; a.ep_shift = ep.shift; a.ep_relu = ep.relu;
   a.Cin = d->Cin; a.Ho = Ho; a.Wo = Wo; a.stride = d->stride; a.ks = d->ksize; a.pad = pad;
   return launch_kernel<BN, true>(tmA, tmA, tmB, tmD, a, st);
@@ -444,6 +446,16 @@ extern "C" int conv1x1_gemm_add(const mvfb_gemm_desc* d, const void* a0, const v
                                 long long ldr, void* out, mvfb_stream_t stream) {
   MVFB_CHECK(res != nullptr, MVFB_ERR_ARG, "conv1x1_gemm_add needs the addend");
   return conv1x1_gemm_impl(d, a0, a1, b, res, ldr, out, nullptr, nullptr, Epi{}, stream);
+}
+
+extern "C" int conv1x1_gemm_add_cols(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, const void* res,
+                                     long long ldr, int first_col, void* out, mvfb_stream_t stream) {
+  MVFB_CHECK(res != nullptr, MVFB_ERR_ARG, "conv1x1_gemm_add_cols needs the addend");
+  MVFB_CHECK(d && first_col >= 0 && first_col % 32 == 0 && first_col < d->N, MVFB_ERR_ARG,
+             "first_col=%d must be a multiple of 32 inside [0, N)", first_col);
+  Epi ep;
+  ep.res_col0 = first_col;
+  return conv1x1_gemm_impl(d, a0, a1, b, res, ldr, out, nullptr, nullptr, ep, stream);
 }
 
 extern "C" int conv1x1_gemm_bnact(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, const float* scale,

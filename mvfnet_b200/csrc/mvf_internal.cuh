@@ -62,7 +62,7 @@ size_t mvf_sweep_bwd_ws(const mvfb_mvf_desc* d);
 int mvf_sweep_bwd(const mvfb_mvf_desc* d, const void* g, long long g_stride, const void* x, void* dx,
                   long long dx_stride, const float* wt, const float* wh, const float* ww, const float* gamma,
                   const float* beta, const float* mean, const float* rstd, float* dwt, float* dwh, float* dww,
-                  float* dgamma, float* dbeta, void* ws, cudaStream_t st);
+                  float* dgamma, float* dbeta, void* ws, const void* dx_add, cudaStream_t st);
 
 // sums (fp64, [11][Cs]) -> fp32 parameter gradients (mvf_generic.cu)
 __global__ void mvf_bwd_finalize(const double* sums, int Cs, int h_shares, int w_shares, int has_h, int has_w,

@@ -19,7 +19,9 @@
 //     the 28 tap-gradient accumulators are shared); whole frames per CTA, channel group as wide as the thread budget
 //     allows: 64 channels at 7 x 7 (128-byte TMA rows), 16 at 14 x 14, 8 at 28 x 28 -- every R50 / R101 slab at 224 px
 //     and the 16 x 16 / 8 x 8 slabs at 256 px.
-//   * temporal terms roll through registers exactly like the forward: dx(t-1) = P(t-1) + kt0 dz(t).
+//   * temporal terms roll through registers like the forward's: a thread keeps its own dz(t-1), dz(t-2) packed, and
+//     dx(t-1) is finished in step t, in the same barrier interval as the computation of dz(t) (one consumer barrier
+//     per frame, two independent dependency chains per item between barriers).
 // dx may alias g (include/mvf_b200.h): a frame of g is in shared memory before any dx of that frame is written, and
 // the frames a CTA re-reads in sweep 1 are never frames whose dx has been written (its own clips, in order).
 #include <cuda_bf16.h>
@@ -66,6 +68,7 @@ struct WArgs {
   float *dwt, *dwh, *dww, *dgamma, *dbeta;
   __nv_bfloat16* dx;
   long long dx_pix;
+  const __nv_bfloat16* dx_add;   // optional: dx += dx_add (addressed like dx): the gradient of the block's identity path
 };
 
 struct P4 {               // 4 bf16 channels, packed as loaded
@@ -388,29 +391,48 @@ mvf_sweep_bwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
   const uint32_t dz0 = smem_u32(c.dz), dzb = (uint32_t)g.slot_x;
   const size_t frame_elems = (size_t)HW * a.dx_pix;
   uint32_t par = 0;                                             // which dz buffer this frame writes
+  // dx(s) = kc dz(s) + kt2 dz(s-1) + kt0 dz(s+1) + kh0 dz(s)[h+1] + kh2 dz(s)[h-1] + kw0 dz(s)[w+1] + kw2 dz(s)[w-1]
+  // (the transposed stencil).  The H / W neighbours of dz(s) come from the shared-memory frame that step s filled and
+  // the barrier at the end of step s published; the three temporal terms are this thread's own registers.  It runs in
+  // step s + 1, in the same barrier interval as the computation of dz(s+1): two independent dependency chains per item.
+  auto finish = [&](int i, uint32_t dzbuf, const P4& d0, const P4& dm, const P4& dp, __nv_bfloat16* dst) {
+    float2 o[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+    if (a.dx_add) {
+      const uint2 q = __ldg(reinterpret_cast<const uint2*>(a.dx_add + (dst - a.dx) + pixoff[i]));
+      o[0] = make_float2(bf16_lo(q.x), bf16_hi(q.x));
+      o[1] = make_float2(bf16_lo(q.y), bf16_hi(q.y));
+    }
+    const uint32_t dc = dzbuf + off[i];
+    const P4 n0 = lds_p4(dc + rowb), n1 = lds_p4(dc - rowb), n2 = lds_p4(dc + pixb), n3 = lds_p4(dc - pixb);
+    fh4(o, d0, kc); fh4(o, d0, kcl);
+    fh4(o, dm, kt2); fh4(o, dp, kt0);
+    fh4(o, n0, kh0); fh4(o, n1, kh2);
+    fh4(o, n2, kw0); fh4(o, n3, kw2);
+    uint2 w2;
+    w2.x = pack_bf16(o[0].x, o[0].y); w2.y = pack_bf16(o[1].x, o[1].y);
+    *reinterpret_cast<uint2*>(dst + pixoff[i]) = w2;
+  };
   for (int kclip = 0; kclip < nclips; ++kclip) {
     __nv_bfloat16* dxf = a.dx + (size_t)(p + kclip * g.P) * g.T * frame_elems;   // frame 0 of this clip
-    P4 xm[IT], xc[IT], dzprev[IT];
-    float2 pprev[IT][2];
+    P4 xm[IT], xc[IT], dz1[IT], dz2[IT];                        // dz(t-1), dz(t-2)
     wait_u32(fb, ph);
 #pragma unroll
     for (int i = 0; i < IT; ++i) {
-      xm[i] = zero_p4(); dzprev[i] = zero_p4();
+      xm[i] = zero_p4(); dz1[i] = zero_p4(); dz2[i] = zero_p4();
       xc[i] = act[i] ? lds_p4(cur + off[i]) : zero_p4();
-      pprev[i][0] = make_float2(0.f, 0.f); pprev[i][1] = make_float2(0.f, 0.f);
     }
 #pragma unroll 1
     for (int t = 0; t < g.T; ++t) {
       uint32_t nxt, fb1, ph1;
       advance(nxt, fb1, ph1);
-      P4 xp[IT], dzp[IT];
+      P4 xp[IT];
       if (t + 1 < g.T) wait_u32(fb1, ph1);
 #pragma unroll
       for (int i = 0; i < IT; ++i) xp[i] = (t + 1 < g.T && act[i]) ? lds_p4(nxt + off[i]) : zero_p4();
-      const uint32_t dzw = dz0 + par * dzb;
+      const uint32_t dzw = dz0 + par * dzb, dzr = dz0 + (par ^ 1u) * dzb;
 #pragma unroll
       for (int i = 0; i < IT; ++i) {
-        dzp[i] = zero_p4();
+        P4 dzp = zero_p4();
         if (act[i]) {
           float2 z[2];
           P4 xhm, xhp, xwm, xwp;
@@ -426,58 +448,34 @@ mvf_sweep_bwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
               du.y = bf16_hi(gq.v[j]) * hswish_grad_f(u.y);
               dzf[j] = __ffma2_rn(scale[j], du, __ffma2_rn(u, c1v[j], c0v[j]));
             }
-            dzp[i].v[0] = pack_bf16(dzf[0].x, dzf[0].y);
-            dzp[i].v[1] = pack_bf16(dzf[1].x, dzf[1].y);
+            dzp.v[0] = pack_bf16(dzf[0].x, dzf[0].y);
+            dzp.v[1] = pack_bf16(dzf[1].x, dzf[1].y);
           } else {
-            dzp[i] = gq;                                         // y = z: dz is the incoming gradient itself
+            dzp = gq;                                            // y = z: dz is the incoming gradient itself
           }
-          fh4(acc[0], dzp[i], xc[i]);
-          fh4(acc[1], dzp[i], xm[i]);
-          fh4(acc[2], dzp[i], xp[i]);
-          fh4(acc[3], dzp[i], xhm);
-          fh4(acc[4], dzp[i], xhp);
-          fh4(acc[5], dzp[i], xwm);
-          fh4(acc[6], dzp[i], xwp);
-          sts_p4(dzw + off[i], dzp[i]);
+          fh4(acc[0], dzp, xc[i]);
+          fh4(acc[1], dzp, xm[i]);
+          fh4(acc[2], dzp, xp[i]);
+          fh4(acc[3], dzp, xhm);
+          fh4(acc[4], dzp, xhp);
+          fh4(acc[5], dzp, xwm);
+          fh4(acc[6], dzp, xwp);
+          sts_p4(dzw + off[i], dzp);
+          if (t > 0) finish(i, dzr, dz1[i], dz2[i], dzp, dxf + (size_t)(t - 1) * frame_elems);
         }
+        dz2[i] = dz1[i]; dz1[i] = dzp;
+        xm[i] = xc[i]; xc[i] = xp[i];
       }
       __syncwarp();
       if (lane == 0) arrive_u32(empty0 + (fb - full0));          // x(t) neighbours and g(t) are consumed
       consumer_bar_sync(nconsumer);                              // dz(t) of every pixel is in shared memory
-#pragma unroll
-      for (int i = 0; i < IT; ++i) {
-        if (act[i]) {
-          if (t > 0) {                                           // dx(t-1) = P(t-1) + kt0 dz(t)
-            float2 o[2] = {pprev[i][0], pprev[i][1]};
-            fh4(o, dzp[i], kt0);
-            uint2 w2;
-            w2.x = pack_bf16(o[0].x, o[0].y); w2.y = pack_bf16(o[1].x, o[1].y);
-            *reinterpret_cast<uint2*>(dxf + (size_t)(t - 1) * frame_elems + pixoff[i]) = w2;
-          }
-          float2 pn[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-          const uint32_t dc = dzw + off[i];
-          fh4(pn, dzp[i], kc); fh4(pn, dzp[i], kcl);
-          fh4(pn, dzprev[i], kt2);
-          fh4(pn, lds_p4(dc + rowb), kh0);
-          fh4(pn, lds_p4(dc - rowb), kh2);
-          fh4(pn, lds_p4(dc + pixb), kw0);
-          fh4(pn, lds_p4(dc - pixb), kw2);
-          pprev[i][0] = pn[0]; pprev[i][1] = pn[1];
-          dzprev[i] = dzp[i];
-        }
-        xm[i] = xc[i]; xc[i] = xp[i];
-      }
       par ^= 1;
       cur = nxt; fb = fb1; ph = ph1;
     }
+    // dx(T-1): there is no frame T.  dz(T-1) sits in the buffer the last step wrote (par was flipped after it).
 #pragma unroll
-    for (int i = 0; i < IT; ++i) {
-      if (act[i]) {                                              // dx(T-1): there is no frame T
-        uint2 w2;
-        w2.x = pack_bf16(pprev[i][0].x, pprev[i][0].y); w2.y = pack_bf16(pprev[i][1].x, pprev[i][1].y);
-        *reinterpret_cast<uint2*>(dxf + (size_t)(g.T - 1) * frame_elems + pixoff[i]) = w2;
-      }
-    }
+    for (int i = 0; i < IT; ++i)
+      if (act[i]) finish(i, dz0 + (par ^ 1u) * dzb, dz1[i], dz2[i], zero_p4(), dxf + (size_t)(g.T - 1) * frame_elems);
   }
 
   // ---- tap gradients: reduce over the CTA, then one atomic per (channel, tap) (the outputs were zeroed before the launch)
@@ -627,9 +625,10 @@ size_t mvf_sweep_bwd_ws(const mvfb_mvf_desc* d) {
 int mvf_sweep_bwd(const mvfb_mvf_desc* d, const void* gp, long long g_stride, const void* x, void* dx,
                   long long dx_stride, const float* wt, const float* wh, const float* ww, const float* gamma,
                   const float* beta, const float* mean, const float* rstd, float* dwt, float* dwh, float* dww,
-                  float* dgamma, float* dbeta, void* ws, cudaStream_t st) {
+                  float* dgamma, float* dbeta, void* ws, const void* dx_add, cudaStream_t st) {
   WGeo g;
   if (!choose(d, g)) return MVFB_ERR_UNSUPPORTED;
+  if ((uintptr_t)dx_add & 7) return MVFB_ERR_UNSUPPORTED;
   if (((uintptr_t)x & 15) || ((uintptr_t)gp & 15) || ((uintptr_t)dx & 7) || g_stride % 8 != 0 || dx_stride % 4 != 0 ||
       (long long)d->H * d->W * dx_stride + d->Cs >= (1LL << 32))
     return MVFB_ERR_UNSUPPORTED;
@@ -650,6 +649,7 @@ int mvf_sweep_bwd(const mvfb_mvf_desc* d, const void* gp, long long g_stride, co
   a.dwt = dwt; a.dwh = (has_h && !a.share_h) ? dwh : nullptr; a.dww = (has_w && !a.share_w) ? dww : nullptr;
   a.dgamma = dgamma; a.dbeta = dbeta;
   a.dx = (__nv_bfloat16*)dx; a.dx_pix = dx_stride;
+  a.dx_add = (const __nv_bfloat16*)dx_add;
   MVFB_CUDA(cudaMemsetAsync(dwt, 0, sizeof(float) * 3 * d->Cs, st));
   if (a.dwh) MVFB_CUDA(cudaMemsetAsync(a.dwh, 0, sizeof(float) * 3 * d->Cs, st));
   if (a.dww) MVFB_CUDA(cudaMemsetAsync(a.dww, 0, sizeof(float) * 3 * d->Cs, st));

@@ -274,6 +274,20 @@ class MVF(nn.Module):
             return out if isinstance(out, tuple) else (out, None)
         return out
 
+    def forward_with_identity(self, x):
+        """Bottleneck's fused configuration: (out, sums, identity) with `identity` an alias of x whose gradient is summed
+        inside this module's backward kernels; None when the fused GEMM path does not apply."""
+        from . import ops
+        net = self.net
+        if (self.num_shift_channel != 0 and self.num_shift_channel % 64 == 0 and isinstance(net, nn.Conv2d)
+                and net.kernel_size == (1, 1) and net.stride == (1, 1) and net.bias is None and net.groups == 1
+                and ops.eligible(x, net.in_channels, net.out_channels)):
+            cfg, wt, wh, ww, gamma, beta, rm, rv = self._kernel_args()
+            out = ops.mvf_conv1x1(x, net.weight, wt, wh, ww, gamma, beta, rm, rv, cfg, stats=True, passthrough=True)
+            self._count_batch(cfg)
+            return out
+        return None
+
     def _forward(self, x, with_stats):
         net = self.net
         if (self.num_shift_channel != 0 and self.num_shift_channel % 64 == 0 and isinstance(net, nn.Conv2d)

@@ -67,6 +67,8 @@ def _L():
         L.conv1x1_gemm_bnact.argtypes = [C.POINTER(GemmDesc), _VP, _VP, _VP, _VP, _VP, _VP, _LL, C.c_int, _VP, _VP]
         L.conv3x3_gemm_bnact.restype = C.c_int
         L.conv3x3_gemm_bnact.argtypes = [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, C.c_int, _VP, _VP]
+        L.conv1x1_gemm_add_cols.restype = C.c_int
+        L.conv1x1_gemm_add_cols.argtypes = [C.POINTER(GemmDesc), _VP, _VP, _VP, _VP, _LL, C.c_int, _VP, _VP]
         L.conv1x1_gemm_add.restype = C.c_int
         L.conv1x1_gemm_add.argtypes = [C.POINTER(GemmDesc), _VP, _VP, _VP, _VP, _LL, _VP, _VP]
         L.stem_im2col.restype = C.c_int
@@ -151,6 +153,15 @@ def register_bf16_sources(params, views):
     bump_weight_epoch()
 
 
+# (id(param), form) -> (weak reference, tensor): derived bf16 forms FlatSGD keeps current itself (one batched transpose
+# launch per step, csrc/tail.cu::transpose_tiles): "rowsT" of the 1x1 weights, "rot" of the channels_last 3x3 weights
+_BF16_FORMS = {}
+
+
+def register_bf16_form(param, form, tensor):
+    _BF16_FORMS[(id(param), form)] = (weakref.ref(param), tensor)
+
+
 def _bf16_source(weight):
     hit = _BF16_SOURCES.get(id(weight))
     if hit is not None and hit[0]() is weight and hit[1].device == weight.device:
@@ -165,6 +176,9 @@ def _wform(weight, form):
     if (hit is not None and hit[0]() is weight and hit[1] == ver and hit[2] == _WEIGHT_EPOCH
             and hit[3].device == weight.device):
         return hit[3]
+    kept = _BF16_FORMS.get(key)
+    if kept is not None and kept[0]() is weight and kept[1].device == weight.device:
+        return kept[1]
     if form == "nchw":
         t = _bf16_source(weight)
         if t is None:
@@ -196,6 +210,8 @@ def _wform(weight, form):
             del _WFORMS[k]
         for k in [k for k, v in _BF16_SOURCES.items() if v[0]() is None]:
             del _BF16_SOURCES[k]
+        for k in [k for k, v in _BF16_FORMS.items() if v[0]() is None]:
+            del _BF16_FORMS[k]
     _WFORMS[key] = (weakref.ref(weight), ver, _WEIGHT_EPOCH, t)
     return t
 
@@ -216,9 +232,9 @@ def eligible(x, cin, cout):
             and x.is_contiguous(memory_format=torch.channels_last) and x.shape[1] == cin)
 
 
-def gemm_tn(a1, b, a0=None, k0=0, stats=False, out=None, add=None):
-    """out[m, n] = sum_k A[m, k] b[n, k] (+ add[m, n]) with A = [a0[:, :k0] | a1[:, k0:]]; 2-D bf16 tensors whose last
-    dim is contiguous.  Returns (out, colsum, colsq) -- the sums are None unless `stats`."""
+def gemm_tn(a1, b, a0=None, k0=0, stats=False, out=None, add=None, add_col0=0):
+    """out[m, n] = sum_k A[m, k] b[n, k] (+ add[m, n] for n >= add_col0) with A = [a0[:, :k0] | a1[:, k0:]]; 2-D bf16
+    tensors whose last dim is contiguous.  Returns (out, colsum, colsq) -- the sums are None unless `stats`."""
     L = _L()
     m, k = a1.shape
     n = b.shape[0]
@@ -237,7 +253,11 @@ def gemm_tn(a1, b, a0=None, k0=0, stats=False, out=None, add=None):
     if add is not None:
         assert not stats and add.shape == (m, n) and add.stride(1) == 1 and add.dtype == torch.bfloat16
         with _T("gemm1x1", nbytes=nbytes + 2 * m * n, flops=2 * m * n * k):
-            rc = L.conv1x1_gemm_add(C.byref(d), ptr(a0), ptr(a1), ptr(b), ptr(add), add.stride(0), ptr(out), _stream())
+            if add_col0:
+                rc = L.conv1x1_gemm_add_cols(C.byref(d), ptr(a0), ptr(a1), ptr(b), ptr(add), add.stride(0), add_col0,
+                                             ptr(out), _stream())
+            else:
+                rc = L.conv1x1_gemm_add(C.byref(d), ptr(a0), ptr(a1), ptr(b), ptr(add), add.stride(0), ptr(out), _stream())
         _lib.check(rc, "conv1x1_gemm_add")
         return out, None, None
     with _T("gemm1x1", nbytes=nbytes, flops=2 * m * n * k):
@@ -431,26 +451,31 @@ def conv1x1(x, weight, stats=False, passthrough=False):
 
 
 class _MVFConv1x1(torch.autograd.Function):
-    """MVF.forward (MVF.py:104-138) in two launches: fused MVF kernel -> compact slab; K-split GEMM."""
+    """MVF.forward (MVF.py:104-138) in two launches: fused MVF kernel -> compact slab; K-split GEMM.  `passthrough`: also
+    returns an alias of x that the Bottleneck uses as its identity path, so that the identity's gradient arrives HERE and
+    is summed inside the kernels (conv1x1_gemm_add_cols for the untouched channels, mvf_bwd_add for the slab) instead of
+    by an autograd add over the full tensor."""
 
     @staticmethod
-    def forward(ctx, x, weight, wt, wh, ww, gamma, beta, running_mean, running_var, cfg, stats):
+    def forward(ctx, x, weight, wt, wh, ww, gamma, beta, running_mean, running_var, cfg, stats, passthrough):
         f, c, h, w = x.shape
         slab, xk, layout, save_mean, save_rstd = _mvf.mvf_slab_forward(
             x, cfg, wt, wh, ww, gamma, beta, running_mean, running_var, out="slab")
         wb = _wform(weight, "rows")
         out, colsum, _ = gemm_tn(_rows(xk), wb, a0=_rows(slab), k0=cfg.Cs, stats=stats)
-        ctx.cfg, ctx.layout, ctx.weight = cfg, layout, weight
+        ctx.cfg, ctx.layout, ctx.weight, ctx.passthrough = cfg, layout, weight, passthrough
         ctx.save_for_backward(xk, slab, wb, wt, wh, ww, gamma, beta, running_mean, running_var, save_mean, save_rstd)
-        y = _nhwc_from_rows(out, f, h, w)
-        if not stats:
-            return y
-        sums = colsum._base if colsum._base is not None else colsum
-        ctx.mark_non_differentiable(sums)
-        return y, sums
+        outs = [_nhwc_from_rows(out, f, h, w)]
+        if stats:
+            sums = colsum._base if colsum._base is not None else colsum
+            ctx.mark_non_differentiable(sums)
+            outs.append(sums)
+        if passthrough:
+            outs.append(x.view_as(x))
+        return outs[0] if len(outs) == 1 else tuple(outs)
 
     @staticmethod
-    def backward(ctx, g, *unused):
+    def backward(ctx, g, *rest):
         L = _lib.lib()
         cfg, layout = ctx.cfg, ctx.layout
         xk, slab, wb, wt, wh, ww, gamma, beta, running_mean, running_var, save_mean, save_rstd = ctx.saved_tensors
@@ -458,16 +483,23 @@ class _MVFConv1x1(torch.autograd.Function):
         cs = cfg.Cs
         g = g.contiguous(memory_format=torch.channels_last)
         g2 = _rows(g)
-        # dL/dx' (all C channels) = dY W; the slab columns are then rewritten IN PLACE by mvf_bwd, which reads a
-        # frame of g completely before it writes that frame's dx (kernel contract, include/mvf_b200.h)
-        dxp, _, _ = gemm_tn(g2, _wform(ctx.weight, "rowsT"))
+        d = _mvf._make_desc(xk, layout, cfg)
+        g_id = rest[-1] if ctx.passthrough else None
+        fuse_add = None
+        if g_id is not None:
+            g_id = g_id.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+            if _lib.plan(d, True) == "sweep":
+                fuse_add = _rows(g_id)
+        # dL/dx' (all C channels) = dY W (+ the identity path's gradient on the untouched channels); the slab columns are
+        # then rewritten IN PLACE by mvf_bwd, which reads a frame of g completely before it writes that frame's dx
+        # (kernel contract, include/mvf_b200.h) and adds the identity path's gradient of the slab channels itself
+        dxp, _, _ = gemm_tn(g2, _wform(ctx.weight, "rowsT"), add=fuse_add, add_col0=cs if fuse_add is not None else 0)
         dw = None
         if ctx.needs_input_grad[1]:
             sink = _grad_sink(ctx.weight, (wb.shape[0], c))
             dw = gemm_wgrad(g2, _rows(xk), x0=_rows(slab), k0=cs, out=sink)
             dw = sink if sink is not None else dw.view(wb.shape[0], c, 1, 1)
         dx = _nhwc_from_rows(dxp, f, h, w)
-        d = _mvf._make_desc(xk, layout, cfg)
         dev = xk.device
         dwt = torch.empty((cs, 3), dtype=torch.float32, device=dev)
         dwh = torch.empty_like(dwt) if (wh is not None and wh.data_ptr() != wt.data_ptr()) else None
@@ -476,16 +508,22 @@ class _MVFConv1x1(torch.autograd.Function):
         dbeta = torch.empty_like(dgamma) if cfg.use_hs else None
         nbytes = L.mvf_bwd_workspace_bytes(C.byref(d))
         ws = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=dev)
+        args = (C.byref(d), ptr(dxp), c, ptr(xk), ptr(dxp), c, ptr(wt), ptr(wh), ptr(ww), ptr(gamma), ptr(beta),
+                ptr(running_mean), ptr(running_var), ptr(save_mean), ptr(save_rstd), ptr(dwt), ptr(dwh), ptr(dww),
+                ptr(dgamma), ptr(dbeta), ptr(ws), ws.numel())
         with _mvf._Timed("mvf_bwd", f * cs * h * w, xk.element_size()):
-            rc = L.mvf_bwd(C.byref(d), ptr(dxp), c, ptr(xk), ptr(dxp), c, ptr(wt), ptr(wh), ptr(ww), ptr(gamma),
-                           ptr(beta), ptr(running_mean), ptr(running_var), ptr(save_mean), ptr(save_rstd), ptr(dwt),
-                           ptr(dwh), ptr(dww), ptr(dgamma), ptr(dbeta), ptr(ws), ws.numel(), _mvf._stream())
+            if fuse_add is not None:
+                rc = L.mvf_bwd_add(*args, ptr(fuse_add), _mvf._stream())
+            else:
+                rc = L.mvf_bwd(*args, _mvf._stream())
         _lib.check(rc, "mvf_bwd")
-        return dx, dw, dwt, dwh, dww, dgamma, dbeta, None, None, None, None
+        if g_id is not None and fuse_add is None:
+            dx = dx + g_id                                       # a tier without the fused addend: autograd's add, here
+        return dx, dw, dwt, dwh, dww, dgamma, dbeta, None, None, None, None, None
 
 
-def mvf_conv1x1(x, weight, wt, wh, ww, gamma, beta, running_mean, running_var, cfg, stats=False):
-    return _MVFConv1x1.apply(x, weight, wt, wh, ww, gamma, beta, running_mean, running_var, cfg, stats)
+def mvf_conv1x1(x, weight, wt, wh, ww, gamma, beta, running_mean, running_var, cfg, stats=False, passthrough=False):
+    return _MVFConv1x1.apply(x, weight, wt, wh, ww, gamma, beta, running_mean, running_var, cfg, stats, passthrough)
 
 
 # ------------------------------------------------------------------------------------------------ 3x3 convolution

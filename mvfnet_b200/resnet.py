@@ -32,9 +32,13 @@ def _conv1x1_id(conv, x):
     """conv1 of a Bottleneck in the fused configuration: (out, sums, identity) where `identity` aliases x and carries
     its gradient back into the convolution's own backward (ops._Conv1x1); None when the layer is not eligible."""
     from . import ops
+    from .mvf import MVF
+    if not (x.requires_grad and torch.is_grad_enabled() and ops.add_fusion_enabled()):
+        return None
+    if isinstance(conv, MVF):
+        return conv.forward_with_identity(x)
     if (type(conv) is nn.Conv2d and conv.kernel_size == (1, 1) and conv.stride == (1, 1) and conv.bias is None
-            and conv.groups == 1 and ops.eligible(x, conv.in_channels, conv.out_channels) and x.requires_grad
-            and torch.is_grad_enabled() and ops.add_fusion_enabled()):
+            and conv.groups == 1 and ops.eligible(x, conv.in_channels, conv.out_channels)):
         return ops.conv1x1(x, conv.weight, True, True)
     return None
 

@@ -43,6 +43,8 @@ def _L():
         L.flat_sqnorm.argtypes = [_VP, _LL, _VP, _VP]
         L.sgd_nesterov_step.restype = _I
         L.sgd_nesterov_step.argtypes = [_VP, _VP, _VP, _VP, _LL, _VP, _VP, _F, _F, _F, _F, _F, _I, _VP]
+        L.transpose_tiles.restype = _I
+        L.transpose_tiles.argtypes = [_VP, _LL, _VP]
         _declared = True
     return L
 
@@ -194,9 +196,55 @@ class FlatSGD:
         self.grads.restride(self.params)
         self.flat_p16.copy_(self.flat_p)
         ops.register_bf16_sources(self.params, self._views16)
+        self._build_transposed_forms()
         (views,) = self.grads.views.values()
         ops.register_grad_sinks(self.params, views)            # weight-gradient kernels write into the flat buffer
         self.steps = 0
+
+    def _build_transposed_forms(self):
+        """The W^T operands of the input-gradient GEMMs ((Cin, Cout) for 1x1 weights; (Cin, 3, 3, Cout) with the taps
+        rotated by 180 degrees for channels_last 3x3 weights) live in a second flat bf16 buffer; a table of 32 x 32
+        tiles, built once, lets ONE transpose_tiles launch per step rebuild all of them from the flat bf16 weights."""
+        import numpy as np
+        jobs, total = [], 0                                     # (param, view16, form, shape of the form)
+        for p, v in zip(self.params, self._views16):
+            if p.dim() != 4 or p.shape[0] % 64 or p.shape[1] % 64:
+                continue
+            if p.shape[2] == p.shape[3] == 1:
+                jobs.append((p, v, "rowsT", (p.shape[1], p.shape[0])))
+            elif p.shape[2] == p.shape[3] == 3 and p.is_contiguous(memory_format=torch.channels_last):
+                jobs.append((p, v, "rot", (p.shape[1], 3, 3, p.shape[0])))
+            else:
+                continue
+            total += p.numel()
+        self._tiles, self._ntiles = None, 0
+        if not jobs:
+            return
+        self.flat_p16T = torch.zeros(total, dtype=torch.bfloat16, device=self.flat_p.device)
+        rec = np.dtype([("src", "<u8"), ("dst", "<u8"), ("lds", "<i4"), ("ldd", "<i4"), ("rows", "<i4"), ("cols", "<i4"),
+                        ("r0", "<i4"), ("c0", "<i4")])
+        tiles, off = [], 0
+        for p, v, form, shape in jobs:
+            cout, cin = p.shape[0], p.shape[1]
+            dst = self.flat_p16T[off:off + p.numel()].view(shape)
+            off += p.numel()
+            ops.register_bf16_form(p, form, dst)
+            taps = 1 if form == "rowsT" else 9
+            for tap in range(taps):                              # source tap (r, s) -> destination tap (2 - r, 2 - s)
+                src = v.data_ptr() + 2 * tap * cin
+                dptr = dst.data_ptr() + 2 * (taps - 1 - tap) * cout
+                for r0 in range(0, cout, 32):
+                    for c0 in range(0, cin, 32):
+                        tiles.append((src, dptr, taps * cin, taps * cout, cout, cin, r0, c0))
+        table = np.array(tiles, dtype=rec)
+        self._tiles = torch.from_numpy(table.view(np.uint8).copy()).to(self.flat_p.device)
+        self._ntiles = len(tiles)
+        self._transpose()
+
+    def _transpose(self):
+        if self._ntiles:
+            with _T("optimizer", nbytes=4 * self.flat_p16T.numel()):
+                _lib.check(_L().transpose_tiles(ptr(self._tiles), self._ntiles, _stream()), "transpose_tiles")
 
     def zero_grad(self, set_to_none=True):
         self.grads.zero_()
@@ -225,6 +273,7 @@ class FlatSGD:
                                      float(d["lr"]), float(d["momentum"]), float(d["weight_decay"]), int(bool(d["nesterov"])),
                                      _stream())
         _lib.check(rc, "sgd_nesterov_step")
+        self._transpose()                                                      # W^T / rotated operands of the next backward
         ops.bump_weight_epoch()                                                # derived bf16 forms (W^T, KRSC, ...) are stale
         self.steps += 1
 

@@ -148,3 +148,7 @@ def test_flat_sgd_golden_and_vs_torch():
     from mvfnet_b200 import ops
     assert torch.equal(ops._wform(a[1], "rows"), a[1].detach().reshape(256, 64).to(torch.bfloat16))
     assert torch.equal(ops._wform(a[2], "krsc"), a[2].detach().permute(0, 2, 3, 1).to(torch.bfloat16))
+    # ... and so are the transposed / rotated input-gradient operands (one transpose_tiles launch per step)
+    assert torch.equal(ops._wform(a[1], "rowsT"), a[1].detach().reshape(256, 64).to(torch.bfloat16).t())
+    assert torch.equal(ops._wform(a[2], "rot"), a[2].detach().to(torch.bfloat16).flip(2, 3).permute(1, 2, 3, 0))
+    assert ops._wform(a[1], "rowsT").is_contiguous() and ops._wform(a[2], "rot").is_contiguous()
