@@ -395,13 +395,10 @@ mvf_sweep_bwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
   // (the transposed stencil).  The H / W neighbours of dz(s) come from the shared-memory frame that step s filled and
   // the barrier at the end of step s published; the three temporal terms are this thread's own registers.  It runs in
   // step s + 1, in the same barrier interval as the computation of dz(s+1): two independent dependency chains per item.
-  auto finish = [&](int i, uint32_t dzbuf, const P4& d0, const P4& dm, const P4& dp, __nv_bfloat16* dst) {
-    float2 o[2] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-    if (a.dx_add) {
-      const uint2 q = __ldg(reinterpret_cast<const uint2*>(a.dx_add + (dst - a.dx) + pixoff[i]));
-      o[0] = make_float2(bf16_lo(q.x), bf16_hi(q.x));
-      o[1] = make_float2(bf16_lo(q.y), bf16_hi(q.y));
-    }
+  // `addq`: the identity path's gradient of this item (mvf_bwd_add), requested at the TOP of the step -- a global load
+  // inside the dependency chain of finish() costs a DRAM round trip per frame (measured: +100 us per launch)
+  auto finish = [&](int i, uint32_t dzbuf, const P4& d0, const P4& dm, const P4& dp, __nv_bfloat16* dst, const uint2& addq) {
+    float2 o[2] = {make_float2(bf16_lo(addq.x), bf16_hi(addq.x)), make_float2(bf16_lo(addq.y), bf16_hi(addq.y))};
     const uint32_t dc = dzbuf + off[i];
     const P4 n0 = lds_p4(dc + rowb), n1 = lds_p4(dc - rowb), n2 = lds_p4(dc + pixb), n3 = lds_p4(dc - pixb);
     fh4(o, d0, kc); fh4(o, d0, kcl);
@@ -426,6 +423,13 @@ mvf_sweep_bwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
       uint32_t nxt, fb1, ph1;
       advance(nxt, fb1, ph1);
       P4 xp[IT];
+      uint2 addq[IT];
+#pragma unroll
+      for (int i = 0; i < IT; ++i) {
+        addq[i] = make_uint2(0u, 0u);
+        if (a.dx_add && t > 0 && act[i])
+          addq[i] = __ldg(reinterpret_cast<const uint2*>(a.dx_add + (dxf - a.dx) + (size_t)(t - 1) * frame_elems + pixoff[i]));
+      }
       if (t + 1 < g.T) wait_u32(fb1, ph1);
 #pragma unroll
       for (int i = 0; i < IT; ++i) xp[i] = (t + 1 < g.T && act[i]) ? lds_p4(nxt + off[i]) : zero_p4();
@@ -461,7 +465,7 @@ mvf_sweep_bwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
           fh4(acc[5], dzp, xwm);
           fh4(acc[6], dzp, xwp);
           sts_p4(dzw + off[i], dzp);
-          if (t > 0) finish(i, dzr, dz1[i], dz2[i], dzp, dxf + (size_t)(t - 1) * frame_elems);
+          if (t > 0) finish(i, dzr, dz1[i], dz2[i], dzp, dxf + (size_t)(t - 1) * frame_elems, addq[i]);
         }
         dz2[i] = dz1[i]; dz1[i] = dzp;
         xm[i] = xc[i]; xc[i] = xp[i];
@@ -473,9 +477,16 @@ mvf_sweep_bwd_kernel(const __grid_constant__ CUtensorMap tmx, const __grid_const
       cur = nxt; fb = fb1; ph = ph1;
     }
     // dx(T-1): there is no frame T.  dz(T-1) sits in the buffer the last step wrote (par was flipped after it).
+    uint2 addl[IT];
+#pragma unroll
+    for (int i = 0; i < IT; ++i) {
+      addl[i] = make_uint2(0u, 0u);
+      if (a.dx_add && act[i])
+        addl[i] = __ldg(reinterpret_cast<const uint2*>(a.dx_add + (dxf - a.dx) + (size_t)(g.T - 1) * frame_elems + pixoff[i]));
+    }
 #pragma unroll
     for (int i = 0; i < IT; ++i)
-      if (act[i]) finish(i, dz0 + (par ^ 1u) * dzb, dz1[i], dz2[i], zero_p4(), dxf + (size_t)(g.T - 1) * frame_elems);
+      if (act[i]) finish(i, dz0 + (par ^ 1u) * dzb, dz1[i], dz2[i], zero_p4(), dxf + (size_t)(g.T - 1) * frame_elems, addl[i]);
   }
 
   // ---- tap gradients: reduce over the CTA, then one atomic per (channel, tap) (the outputs were zeroed before the launch)
