@@ -543,7 +543,37 @@ def run_ours(args):
         sweep["B%d" % b] = world * b * n / (timed(dimg, dlbl, n) / 1e3)
         del himg, hlbl, dimg, dlbl
 
+    # ---- the same step captured ONCE into a CUDA graph and replayed (mvfnet_b200/graph.py): what the step costs when the
+    # host is out of the way -- decisive at the recipe's B = 12, where Python + autograd cannot issue ~620 launches as
+    # fast as the GPU retires them
     import gc
+    graphed = None
+    if not args.no_graph and (world == 1 or os.environ.get("MVFB_GRAPH_DDP") == "1"):
+        from mvfnet_b200.graph import GraphedTrainStep
+        graphed = {}
+        for b in [B] + [int(v) for v in args.sweep.split(",") if v and int(v) != B]:
+            try:
+                gc.collect()
+                torch.cuda.empty_cache()
+                himg, hlbl = make_batches(b, 5000)
+                dimg, dlbl = [h.to(dev) for h in himg], [h.to(dev) for h in hlbl]
+                step = GraphedTrainStep(model, opt, dimg[0], dlbl[0], world=world, uint8_input=u8)
+                n = max(6, min(args.steps, 20))
+                for i in range(2):
+                    step(dimg[i % 2], dlbl[i % 2])
+                barrier()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for i in range(n):
+                    step(dimg[i % 2], dlbl[i % 2])
+                g1.record()
+                barrier()
+                graphed["B%d" % b] = world * b * n / (max_over_ranks(g0.elapsed_time(g1)) / 1e3)
+                del step, himg, hlbl, dimg, dlbl
+            except Exception as e:                               # capture is an optimisation, never a requirement
+                graphed["B%d" % b] = None
+                graphed["error_B%d" % b] = repr(e)[:300]
+                break
     del model, opt
     gc.collect()
     torch.cuda.empty_cache()
@@ -563,6 +593,8 @@ def run_ours(args):
         for b in (12, 64):
             if bar.get("B%d" % b) and sweep.get("B%d" % b):
                 bar["ratio_B%d" % b] = sweep["B%d" % b] / bar["B%d" % b]
+            if bar.get("B%d" % b) and graphed and graphed.get("B%d" % b):
+                bar["ratio_B%d_cuda_graph" % b] = graphed["B%d" % b] / bar["B%d" % b]
         best_ref = max([v for k, v in bar.items() if k.startswith("B") and isinstance(v, float)], default=None)
         if best_ref:
             bar["value"], bar["unit"] = best_ref, "clips/s"
@@ -627,6 +659,9 @@ def run_ours(args):
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_by_family": by_family,
             "sweep": sweep}
+    if graphed is not None:
+        line["cuda_graph_step"] = dict(graphed, how="the identical step (uint8 frames -> loss -> backward -> clip -> SGD) captured once, "
+                                       "replayed per batch incl. the device-side copy of the batch into the graph's input")
     if bar is not None:
         line["gpu_bar"] = bar
     if others is not None:
@@ -656,6 +691,7 @@ def main():
     ap.add_argument("--input", default="u8", choices=["u8", "f32"],
                     help="u8: decoded uint8 frames, normalised on the GPU; f32: the reference's float32 wire format")
     ap.add_argument("--sweep", default="12,64", help="extra clips-per-GPU sizes our arm is also timed at (resident inputs)")
+    ap.add_argument("--no-graph", action="store_true", help="skip the CUDA-graph replay measurement of the step")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the short runs of BASELINE.json configs[2..4]")
     ap.add_argument("--no-gpu-bar", action="store_true", help="skip the reference-on-PyTorch/cuDNN arm (gpu_bar)")
     ap.add_argument("--kernels-only", action="store_true",

@@ -284,7 +284,9 @@ int preprocess_u8(const void* x, void* y, long long pixels, const float* mean, c
  *
  *   head_pool_fwd : feat[f, c] = dropout_p( mean over the HW pixels of x[f, :, c] )   x (F, HW, C) bf16 NHWC -> (F, C) bf16
  *                   (the keep decision of element (f, c) is a counter-based hash of (seed, f*C + c): the backward
- *                   recomputes it, no mask is stored; p = 0 disables dropout)
+ *                   recomputes it, no mask is stored; p = 0 disables dropout.  seed_dev (optional DEVICE pointer) is
+ *                   mixed into the seed by the kernel: a step captured in a CUDA graph advances that word on the
+ *                   device, so every replay draws a new mask)
  *   head_ce_fwd   : s[b, c] = bias[c] + mean_t logits[b*T + t, c]  (SimpleConsensus 'avg' over the T segments);
  *                   loss = mean_b ( logsumexp(s[b]) - s[b, label[b]] );  ds = d loss / d s  (B, NC) fp32;
  *                   dbias[c] = sum_b ds[b, c];  score (optional) receives s.  loss / dbias are zeroed by the call.
@@ -293,9 +295,9 @@ int preprocess_u8(const void* x, void* y, long long pixels, const float* mean, c
  *   head_pool_bwd : dx[f, q, c] = dfeat[f, c] * keep(f, c) / ((1 - p) * HW)  for every pixel q.
  * ---------------------------------------------------------------------------------------------- */
 int head_pool_fwd(const void* x, void* feat, long long F, int HW, int C, float p, unsigned long long seed,
-                  mvfb_stream_t stream);
+                  const unsigned long long* seed_dev, mvfb_stream_t stream);
 int head_pool_bwd(const void* dfeat, void* dx, long long F, int HW, int C, float p, unsigned long long seed,
-                  mvfb_stream_t stream);
+                  const unsigned long long* seed_dev, mvfb_stream_t stream);
 int head_ce_fwd(const void* logits, long long ldl, const float* bias, const long long* labels, int B, int T, int NC,
                 float* score, float* ds, float* dbias, float* loss, mvfb_stream_t stream);
 int head_ce_bwd(const float* ds, const float* gout, void* dlogits, long long ldl, int B, int T, int NC,

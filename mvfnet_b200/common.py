@@ -25,33 +25,26 @@ class HardSwish(nn.Module):
         return x * self.sigmoid(x)
 
 
-norm_cfg = {'BN': ('bn', nn.BatchNorm2d), 'BN3d': ('bn', nn.BatchNorm3d), 'GN': ('gn', nn.GroupNorm)}
+# the MVFNet configs build every norm layer as dict(type='BN', requires_grad=True) (r50_dense.py:27)
+norm_cfg = {'BN': ('bn', nn.BatchNorm2d), 'BN3d': ('bn', nn.BatchNorm3d)}
 
 
 def get_norm_type(cfg):
-    assert isinstance(cfg, dict) and 'type' in cfg
     if cfg['type'] not in norm_cfg:
         raise KeyError('Unrecognized norm type {}'.format(cfg['type']))
     return norm_cfg[cfg['type']][1]
 
 
 def build_norm_layer(cfg, num_features, postfix=''):
-    """-> (name, layer): 'bn1', nn.BatchNorm2d(num_features, eps=1e-5) ... (norm.py:28-71)."""
-    assert isinstance(cfg, dict) and 'type' in cfg
-    cfg_ = cfg.copy()
-    layer_type = cfg_.pop('type')
-    if layer_type not in norm_cfg:
-        raise KeyError('Unrecognized norm type {}'.format(layer_type))
-    abbr, norm_layer = norm_cfg[layer_type]
-    assert isinstance(postfix, (int, str))
-    name = abbr + str(postfix)
-    requires_grad = cfg_.pop('requires_grad', True)
-    cfg_.setdefault('eps', 1e-5)
-    if layer_type != 'GN':
-        layer = norm_layer(num_features, **cfg_)
-    else:
-        assert 'num_groups' in cfg_
-        layer = norm_layer(num_channels=num_features, **cfg_)
-    for param in layer.parameters():
-        param.requires_grad = requires_grad
-    return name, layer
+    """-> ('bn<postfix>', layer): the sub-module names `bn1..3` are part of the state_dict contract (norm.py:28-71);
+    eps defaults to 1e-5, `requires_grad` freezes gamma / beta."""
+    kw = dict(cfg)
+    abbr, cls = norm_cfg[kw.pop('type')] if kw.get('type') in norm_cfg else (None, None)
+    if cls is None:
+        raise KeyError('Unrecognized norm type {}'.format(cfg.get('type')))
+    requires_grad = kw.pop('requires_grad', True)
+    kw.setdefault('eps', 1e-5)
+    layer = cls(num_features, **kw)
+    for p in layer.parameters():
+        p.requires_grad = requires_grad
+    return abbr + str(postfix), layer

@@ -107,7 +107,8 @@ __device__ __forceinline__ bool keep_elem(unsigned long long seed, unsigned long
 // x: (F, HW, C) bf16; feat: (F, C) bf16 = dropout(mean over HW).  One thread per (f, 8-channel vector).
 __global__ void __launch_bounds__(kThreads)
 head_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ feat, long long F, int HW, int C,
-                     float p, unsigned long long seed) {
+                     float p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+  if (seed_dev) seed ^= *seed_dev * 0xD6E8FEB86659FD93ull;          // per-replay part of the seed (CUDA-graph steps)
   const int vecs = C >> 3;
   const long long total = F * vecs;
   const float inv_hw = 1.f / (float)HW, keep_scale = p > 0.f ? 1.f / (1.f - p) : 1.f;
@@ -139,7 +140,8 @@ head_pool_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restr
 // dfeat: (F, C) bf16 -> dx: (F, HW, C) bf16 = dfeat * keep / HW broadcast over the HW pixels
 __global__ void __launch_bounds__(kThreads)
 head_pool_bwd_kernel(const __nv_bfloat16* __restrict__ dfeat, __nv_bfloat16* __restrict__ dx, long long F, int HW, int C,
-                     float p, unsigned long long seed) {
+                     float p, unsigned long long seed, const unsigned long long* __restrict__ seed_dev) {
+  if (seed_dev) seed ^= *seed_dev * 0xD6E8FEB86659FD93ull;
   const int vecs = C >> 3;
   const long long total = F * vecs;
   const float scale = (p > 0.f ? 1.f / (1.f - p) : 1.f) / (float)HW;
@@ -320,26 +322,26 @@ int preprocess_u8(const void* x, void* y, long long pixels, const float* mean, c
 }
 
 int head_pool_fwd(const void* x, void* feat, long long F, int HW, int C, float p, unsigned long long seed,
-                  mvfb_stream_t stream) {
+                  const unsigned long long* seed_dev, mvfb_stream_t stream) {
   MVFB_CHECK(x && feat && F > 0 && HW > 0 && C > 0, MVFB_ERR_ARG, "null argument / bad shape");
   MVFB_CHECK(C % 8 == 0 && !((uintptr_t)x & 15) && !((uintptr_t)feat & 15), MVFB_ERR_UNSUPPORTED,
              "C must be a multiple of 8, tensors 16-byte aligned");
   MVFB_CHECK(p >= 0.f && p < 1.f, MVFB_ERR_ARG, "dropout ratio %f outside [0, 1)", p);
   head_pool_fwd_kernel<<<stream_grid(F * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)x, (__nv_bfloat16*)feat, F, HW, C, p, seed);
+      (const __nv_bfloat16*)x, (__nv_bfloat16*)feat, F, HW, C, p, seed, seed_dev);
   count_launch();
   MVFB_LAUNCH_CHECK();
   return MVFB_OK;
 }
 
 int head_pool_bwd(const void* dfeat, void* dx, long long F, int HW, int C, float p, unsigned long long seed,
-                  mvfb_stream_t stream) {
+                  const unsigned long long* seed_dev, mvfb_stream_t stream) {
   MVFB_CHECK(dfeat && dx && F > 0 && HW > 0 && C > 0, MVFB_ERR_ARG, "null argument / bad shape");
   MVFB_CHECK(C % 8 == 0 && !((uintptr_t)dfeat & 15) && !((uintptr_t)dx & 15), MVFB_ERR_UNSUPPORTED,
              "C must be a multiple of 8, tensors 16-byte aligned");
   MVFB_CHECK(p >= 0.f && p < 1.f, MVFB_ERR_ARG, "dropout ratio %f outside [0, 1)", p);
   head_pool_bwd_kernel<<<stream_grid(F * (C / 8)), kThreads, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)dfeat, (__nv_bfloat16*)dx, F, HW, C, p, seed);
+      (const __nv_bfloat16*)dfeat, (__nv_bfloat16*)dx, F, HW, C, p, seed, seed_dev);
   count_launch();
   MVFB_LAUNCH_CHECK();
   return MVFB_OK;

@@ -18,6 +18,7 @@ import torch.nn as nn
 
 from . import _lib
 from ._lib import MvfDesc, ptr
+from .common import HardSwish
 
 
 # Optional launch timing used by bench.py: while a list is installed here every library call of the hot path is
@@ -195,7 +196,8 @@ class MVF(nn.Module):
             self.shift_conv = nn.Conv3d(cs, cs, [3, 1, 1], stride=1, padding=[1, 0, 0], groups=cs, bias=False)
             self.bn = nn.BatchNorm3d(cs)
             self.use_hs = use_hs
-            self.activation = None
+            # same attribute as the reference (MVF.py:71); the kernels apply it, the module is never called
+            self.activation = HardSwish() if use_hs else nn.ReLU(inplace=True)
             self.mode = mode
             if mode not in ('THW', 'T', 'TH'):
                 raise ValueError("mode must be one of 'THW', 'T', 'TH', got %r" % (mode,))

@@ -34,7 +34,7 @@ def _L():
         L.preprocess_u8.argtypes = [_VP, _VP, _LL, C.POINTER(_F), C.POINTER(_F), _I, _VP]
         for fn in (L.head_pool_fwd, L.head_pool_bwd):
             fn.restype = _I
-            fn.argtypes = [_VP, _VP, _LL, _I, _I, _F, C.c_ulonglong, _VP]
+            fn.argtypes = [_VP, _VP, _LL, _I, _I, _F, C.c_ulonglong, _VP, _VP]
         L.head_ce_fwd.restype = _I
         L.head_ce_fwd.argtypes = [_VP, _LL, _VP, _VP, _I, _I, _I, _VP, _VP, _VP, _VP, _VP]
         L.head_ce_bwd.restype = _I
@@ -92,13 +92,14 @@ class _HeadLoss(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, labels, num_seg, p, seed):
         L = _L()
+        ctx.seed_dev = DEVICE_SEED
         f, c, h, w = x.shape
         hw, b = h * w, f // num_seg
         nc = weight.shape[0]
         dev = x.device
         feat = torch.empty((f, c), dtype=torch.bfloat16, device=dev)
         with _T("head", nbytes=2 * (x.numel() + feat.numel())):
-            _lib.check(L.head_pool_fwd(ptr(x), ptr(feat), f, hw, c, p, seed, _stream()), "head_pool_fwd")
+            _lib.check(L.head_pool_fwd(ptr(x), ptr(feat), f, hw, c, p, seed, ptr(ctx.seed_dev), _stream()), "head_pool_fwd")
         wpad = _fc_padded(weight)
         logits, _, _ = ops.gemm_tn(feat, wpad)                                  # (F, ceil64(NC)) bf16
         ds = torch.empty((b, nc), dtype=torch.float32, device=dev)
@@ -131,11 +132,13 @@ class _HeadLoss(torch.autograd.Function):
         dfeat, _, _ = ops.gemm_tn(dlogits, ops._wform(weight, "fcpadT"))         # (F, K) bf16 = dlogits W
         dx = torch.empty((f, h, w, c), dtype=torch.bfloat16, device=dev)
         with _T("head", nbytes=2 * (dx.numel() + dfeat.numel())):
-            _lib.check(L.head_pool_bwd(ptr(dfeat), ptr(dx), f, h * w, c, p, seed, _stream()), "head_pool_bwd")
+            _lib.check(L.head_pool_bwd(ptr(dfeat), ptr(dx), f, h * w, c, p, seed, ptr(ctx.seed_dev), _stream()), "head_pool_bwd")
         return dx.permute(0, 3, 1, 2), dw.to(weight.dtype), (dbias * gout).to(weight.dtype), None, None, None, None
 
 
-_seed_gen = None
+# Optional int64 device scalar mixed into the dropout seed by the kernels; `graph.GraphedTrainStep` installs one and
+# advances it inside the captured step, so that replays draw fresh masks.
+DEVICE_SEED = None
 
 
 def _next_seed(device):
