@@ -270,6 +270,53 @@ def gpu_bar(dev, world, rank, batches, steps=6, warmup=4):
     return out
 
 
+# --------------------------------------------------------------------------------------- MVF kernels in isolation
+def mvf_isolated(dev, B, peak, iters=8):
+    """The fused MVF kernels alone on the dominant slab (layer3.1-5 / layer4.0: C = 1024, 14 x 14, Cs = 128, T = 8) at the
+    bench's clip count, L2 flushed between launches, CUDA events on the launching stream: achieved algorithmic GB/s
+    (forward 2*E*s, backward 3*E*s) of the eval-mode forward (one sweep), the train-mode forward (statistics sweep +
+    exchange + apply sweep in one cooperative launch) and the train-mode backward."""
+    import torch
+    from mvfnet_b200 import MVF
+    from mvfnet_b200 import mvf as mm
+    from mvfnet_b200.mvf import mvf_slab_forward
+    T, C, H, Cs = 8, 1024, 14, 128
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    x = torch.randn(B * T, H, H, C, device=dev).to(torch.bfloat16).permute(0, 3, 1, 2).requires_grad_(True)
+    g = torch.randn(B * T, H, H, C, device=dev).to(torch.bfloat16).permute(0, 3, 1, 2)
+    E = B * T * Cs * H * H
+    out = {"slab": "C=1024 14x14 Cs=128 T=8, %d clips, L2 flushed" % B}
+    for training in (False, True):
+        m = MVF(torch.nn.Identity(), T, C, alpha=0.125).to(dev).train(training)
+        cfg = m._cfg()
+        wt, wh, ww = (w.detach().float().contiguous() for w in m._taps())
+        ts = []
+        for i in range(iters + 2):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            mvf_slab_forward(x.detach(), cfg, wt, wh, ww, m.bn.weight.detach(), m.bn.bias.detach(), m.bn.running_mean,
+                             m.bn.running_var, out="slab")
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e3)
+        us = sorted(ts[2:])[len(ts[2:]) // 2]
+        key = "fwd_train" if training else "fwd_eval"
+        out[key] = {"us": us, "achieved": 2 * E * 2 / us / 1e3, "frac": 2 * E * 2 / us / 1e3 / peak}
+        if training:
+            y = m.fuse(x)
+            mm.timing_begin()
+            for i in range(iters + 2):
+                flush.zero_()
+                x.grad = None
+                y.backward(g, retain_graph=True)
+            torch.cuda.synchronize()
+            rec = sorted(s0.elapsed_time(s1) * 1e3 for k, b, s0, s1, _ in mm.timing_end()[2:] if k == "mvf_bwd")
+            us = rec[len(rec) // 2]
+            out["bwd_train"] = {"us": us, "achieved": 3 * E * 2 / us / 1e3, "frac": 3 * E * 2 / us / 1e3 / peak}
+    return out
+
+
 # --------------------------------------------------------------------------------------- the other BASELINE.json configs
 def light_train_config(dev, world, rank, depth, t, B, steps=6, warmup=3):
     """configs[2] (R50 16x4) / configs[3] (R101 8x8): the same training step as the headline (uint8 frames, bf16,
@@ -643,6 +690,10 @@ def run_ours(args):
                 "mvf_bwd": {"achieved": a_b, "frac": (a_b / peak) if a_b else None,
                             "avg_launch_us": f_bwd[1] / f_bwd[0] * 1e3 if f_bwd else None,
                             "launches_timed": f_bwd[0] if f_bwd else 0, "algorithmic_bytes": "3*E*s"}}
+    try:
+        roofline["isolated"] = mvf_isolated(dev, B, peak)
+    except Exception as e:                                       # informational only
+        roofline["isolated"] = {"error": repr(e)[:200]}
     cpu = cpu_baseline(args.cpu_seconds) if world == 1 else None
     line = {"metric": METRIC, "value": value, "unit": "clips/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",

@@ -207,6 +207,16 @@ int conv3x3_gemm(const mvfb_conv_desc* d, const void* x, const void* w, void* ou
 int conv3x3_gemm_bnact(const mvfb_conv_desc* d, const void* x, const void* w, const float* scale, const float* shift,
                        const void* res, int relu, void* out, mvfb_stream_t stream);
 
+/* Input gradient of the STRIDE-2 3x3 convolution (conv2 of the first block of layer2/3/4): `d` is the forward layer
+ * (F, H, W, Cin, Cout, stride 2, ksize 3; H, W even), g (F, H/2, W/2, Cout), dx (F, H, W, Cin), all bf16 NHWC.  Four
+ * stride-1 implicit GEMMs, one per parity of the output pixel, with 1x1 / 1x2 / 2x1 / 2x2 windows over g (9 taps in total:
+ * no wasted MAC), each scattering its rows to that parity's pixels of dx.  wq = the four parity operands back to back,
+ * parity p = 2*ph + pw:
+ *   wq_p[c][(dh*kw_p + dw)*Cout + n] = w[n, r(ph, dh), s(pw, dw), c]    (Cin rows, kh_p*kw_p*Cout columns)
+ * with kh_p = 1 + ph, kw_p = 1 + pw, r(0, 0) = 1, r(1, 0) = 2, r(1, 1) = 0 (the same for s) -- mvfnet_b200/ops.py builds
+ * it. */
+int conv3x3s2_dgrad(const mvfb_conv_desc* d, const void* g, const void* wq, void* dx, mvfb_stream_t stream);
+
 /* Its weight gradient: dw[n, r, s, c] = sum_{f,ho,wo} g[f, ho, wo, n] * x[f, ho*stride + r - 1, wo*stride + s - 1, c]
  * (g bf16 (F, Ho, Wo, Cout); dw fp32 (Cout, 3, 3, Cin), zeroed by the call; MN-major MMA operands, the x operand
  * gathered by TMA im2col, split-K fp32 atomics over the pixel axis). */

@@ -661,9 +661,16 @@ int mvf_sweep_bwd(const mvfb_mvf_desc* d, const void* gp, long long g_stride, co
   a.dgamma = dgamma; a.dbeta = dbeta;
   a.dx = (__nv_bfloat16*)dx; a.dx_pix = dx_stride;
   a.dx_add = (const __nv_bfloat16*)dx_add;
-  MVFB_CUDA(cudaMemsetAsync(dwt, 0, sizeof(float) * 3 * d->Cs, st));
-  if (a.dwh) MVFB_CUDA(cudaMemsetAsync(a.dwh, 0, sizeof(float) * 3 * d->Cs, st));
-  if (a.dww) MVFB_CUDA(cudaMemsetAsync(a.dww, 0, sizeof(float) * 3 * d->Cs, st));
+  // the tap-gradient outputs are accumulated with atomics: zero them first (one memset when the caller allocated the
+  // three of them back to back, as mvfnet_b200/ops.py does)
+  const size_t tapb = sizeof(float) * 3 * d->Cs;
+  if (a.dwh == dwt + 3 * d->Cs && a.dww == a.dwh + 3 * d->Cs) {
+    MVFB_CUDA(cudaMemsetAsync(dwt, 0, 3 * tapb, st));
+  } else {
+    MVFB_CUDA(cudaMemsetAsync(dwt, 0, tapb, st));
+    if (a.dwh) MVFB_CUDA(cudaMemsetAsync(a.dwh, 0, tapb, st));
+    if (a.dww) MVFB_CUDA(cudaMemsetAsync(a.dww, 0, tapb, st));
+  }
   switch (g.IT) {
     case 1: return launch<1>(tmx, tmg, a, st);
     case 2: return launch<2>(tmx, tmg, a, st);

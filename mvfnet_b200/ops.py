@@ -69,6 +69,8 @@ def _L():
         L.conv3x3_gemm_bnact.argtypes = [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, C.c_int, _VP, _VP]
         L.conv1x1_gemm_add_cols.restype = C.c_int
         L.conv1x1_gemm_add_cols.argtypes = [C.POINTER(GemmDesc), _VP, _VP, _VP, _VP, _LL, C.c_int, _VP, _VP]
+        L.conv3x3s2_dgrad.restype = C.c_int
+        L.conv3x3s2_dgrad.argtypes = [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP]
         L.conv1x1_gemm_add.restype = C.c_int
         L.conv1x1_gemm_add.argtypes = [C.POINTER(GemmDesc), _VP, _VP, _VP, _VP, _LL, _VP, _VP]
         L.stem_im2col.restype = C.c_int
@@ -96,6 +98,7 @@ _T = _mvf._Timed          # bench.py's per-family launch timing (no-op unless mv
 #   "nchw"   (Cout, Cin, kh, kw) bf16 in the parameter's memory format
 #   "krsc"   (Cout, 3, 3, Cin) bf16 contiguous          3x3 forward operand B (a no-op view for channels_last weights)
 #   "rot"    (Cin, 3, 3, Cout) bf16, taps rotated 180   3x3 stride-1 input-gradient operand B
+#   "s2dgrad" four (Cin, taps*Cout) parity blocks       3x3 stride-2 input-gradient operand (conv3x3s2_dgrad)
 #   "fcpad"  (ceil64(NC), K) bf16, zero rows appended   classification head: classes padded to the GEMM's N granularity
 #   "fcpadT" (K, ceil64(NC)) bf16                       ... its input-gradient operand
 _WFORMS = {}
@@ -194,6 +197,8 @@ def _wform(weight, form):
         t = _wform(weight, "nchw").permute(0, 2, 3, 1).contiguous()
     elif form == "rot":
         t = _wform(weight, "nchw").flip(2, 3).permute(1, 2, 3, 0).contiguous()
+    elif form == "s2dgrad":
+        t = _s2_dgrad_operand(_wform(weight, "nchw"))
     elif form == "fcpad":
         w = _wform(weight, "rows")
         npad = (w.shape[0] + 63) // 64 * 64
@@ -501,9 +506,10 @@ class _MVFConv1x1(torch.autograd.Function):
             dw = sink if sink is not None else dw.view(wb.shape[0], c, 1, 1)
         dx = _nhwc_from_rows(dxp, f, h, w)
         dev = xk.device
-        dwt = torch.empty((cs, 3), dtype=torch.float32, device=dev)
-        dwh = torch.empty_like(dwt) if (wh is not None and wh.data_ptr() != wt.data_ptr()) else None
-        dww = torch.empty_like(dwt) if (ww is not None and ww.data_ptr() != wt.data_ptr()) else None
+        taps = torch.empty((3, cs, 3), dtype=torch.float32, device=dev)       # back to back: one memset in the kernel tier
+        dwt = taps[0]
+        dwh = taps[1] if (wh is not None and wh.data_ptr() != wt.data_ptr()) else None
+        dww = taps[2] if (ww is not None and ww.data_ptr() != wt.data_ptr()) else None
         dgamma = torch.empty(cs, dtype=torch.float32, device=dev) if cfg.use_hs else None
         dbeta = torch.empty_like(dgamma) if cfg.use_hs else None
         nbytes = L.mvf_bwd_workspace_bytes(C.byref(d))
@@ -527,6 +533,11 @@ def mvf_conv1x1(x, weight, wt, wh, ww, gamma, beta, running_mean, running_var, c
 
 
 # ------------------------------------------------------------------------------------------------ 3x3 convolution
+def s2_dgrad_enabled() -> bool:
+    """MVFB_S2DGRAD=0 sends the stride-2 3x3 input gradient back to torch / cuDNN (A/B measurements only)."""
+    return os.environ.get("MVFB_S2DGRAD", "1") != "0"
+
+
 def conv3x3_enabled() -> bool:
     """MVFB_CONV3X3=0 routes the 3x3 convolutions back through torch / cuDNN (A/B measurements only)."""
     return os.environ.get("MVFB_CONV3X3", "1") != "0"
@@ -559,6 +570,33 @@ def conv3x3_raw(x, w_krsc, stride, stats=False):
                             ptr(sums[1]) if stats else None, _stream())
     _lib.check(rc, "conv3x3_gemm")
     return out.permute(0, 3, 1, 2), sums
+
+
+def _s2_dgrad_operand(w):
+    """(Cout, Cin, 3, 3) bf16 -> the four parity operands of conv3x3s2_dgrad back to back (include/mvf_b200.h): parity
+    (ph, pw) reads filter rows r(ph) = [1] | [2, 0] and columns s(pw) likewise, (Cin, taps*Cout) each, K order (tap, n)."""
+    rows = {0: (1,), 1: (2, 0)}
+    parts = []
+    for ph in (0, 1):
+        for pw in (0, 1):
+            taps = torch.stack([w[:, :, r, s] for r in rows[ph] for s in rows[pw]], 0)     # (taps, Cout, Cin)
+            parts.append(taps.permute(2, 0, 1).reshape(-1))                                # (Cin, taps, Cout)
+    return torch.cat(parts).contiguous()
+
+
+def conv3x3s2_dgrad_raw(g, weight, h, w):
+    """dL/dx (F, Cin, h, w) of the stride-2 3x3 convolution from g (F, Cout, h/2, w/2): four parity GEMMs."""
+    L = _L()
+    f, cout = g.shape[0], g.shape[1]
+    cin = weight.shape[1]
+    d = ConvDesc()
+    d.F, d.H, d.W, d.Cin, d.Cout, d.stride, d.ksize = f, h, w, cin, cout, 2, 3
+    wq = _wform(weight, "s2dgrad")
+    dx = torch.empty((f, h, w, cin), dtype=torch.bfloat16, device=g.device)
+    with _T("conv3x3", nbytes=2 * (g.numel() + dx.numel() + 9 * cin * cout), flops=2 * f * (h // 2) * (w // 2) * 9 * cin * cout):
+        rc = L.conv3x3s2_dgrad(C.byref(d), ptr(g), ptr(wq), ptr(dx), _stream())
+    _lib.check(rc, "conv3x3s2_dgrad")
+    return dx.permute(0, 3, 1, 2)
 
 
 def conv3x3_wgrad_raw(g, x, cout, stride, ksize, out=None):
@@ -600,6 +638,9 @@ class _Conv3x3(torch.autograd.Function):
         if need_dx and st == 1:
             # stride-1 input gradient = the same convolution with spatially rotated, channel-transposed weights
             dx, _ = conv3x3_raw(g, _wform(ctx.weight, "rot"), 1)          # (Cin, 3, 3, Cout)
+            need_dx = False
+        elif need_dx and st == 2 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0 and s2_dgrad_enabled():
+            dx = conv3x3s2_dgrad_raw(g, ctx.weight, x.shape[2], x.shape[3])
             need_dx = False
         # own 3x3 wgrad where it is within ~1.2x of cuDNN (Cin >= 256: layer3/4); the 9-tap re-read of dY makes it
         # 1.5-3.7x slower on the 56x56 / 28x28 layers (tools/wgrad_probe.py), which stay on the library this round

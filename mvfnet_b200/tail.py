@@ -217,6 +217,8 @@ class FlatSGD:
                 jobs.append((p, v, "rowsT", (p.shape[1], p.shape[0])))
             elif p.shape[2] == p.shape[3] == 3 and p.is_contiguous(memory_format=torch.channels_last):
                 jobs.append((p, v, "rot", (p.shape[1], 3, 3, p.shape[0])))
+                jobs.append((p, v, "s2dgrad", (p.numel(),)))      # whichever stride the layer runs at picks its form
+                total += p.numel()
             else:
                 continue
             total += p.numel()
@@ -232,6 +234,21 @@ class FlatSGD:
             dst = self.flat_p16T[off:off + p.numel()].view(shape)
             off += p.numel()
             ops.register_bf16_form(p, form, dst)
+            if form == "s2dgrad":
+                # parity (ph, pw) of the stride-2 input gradient (ops._s2_dgrad_operand): (Cin, taps*Cout) blocks with the
+                # filter rows [1] | [2, 0] and columns likewise, K order (tap, n)
+                rows, base = {0: (1,), 1: (2, 0)}, 0
+                for ph in (0, 1):
+                    for pw in (0, 1):
+                        sel = [(r, s) for r in rows[ph] for s in rows[pw]]
+                        for j, (r, s) in enumerate(sel):
+                            src = v.data_ptr() + 2 * (r * 3 + s) * cin
+                            dptr = dst.data_ptr() + 2 * (base + j * cout)
+                            for r0 in range(0, cout, 32):
+                                for c0 in range(0, cin, 32):
+                                    tiles.append((src, dptr, 9 * cin, len(sel) * cout, cout, cin, r0, c0))
+                        base += len(sel) * cout * cin
+                continue
             taps = 1 if form == "rowsT" else 9
             for tap in range(taps):                              # source tap (r, s) -> destination tap (2 - r, 2 - s)
                 src = v.data_ptr() + 2 * tap * cin

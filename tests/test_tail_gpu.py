@@ -152,6 +152,7 @@ def test_flat_sgd_golden_and_vs_torch():
     assert torch.equal(ops._wform(a[1], "rowsT"), a[1].detach().reshape(256, 64).to(torch.bfloat16).t())
     assert torch.equal(ops._wform(a[2], "rot"), a[2].detach().to(torch.bfloat16).flip(2, 3).permute(1, 2, 3, 0))
     assert ops._wform(a[1], "rowsT").is_contiguous() and ops._wform(a[2], "rot").is_contiguous()
+    assert torch.equal(ops._wform(a[2], "s2dgrad"), ops._s2_dgrad_operand(a[2].detach().to(torch.bfloat16)))
 
 
 def test_graphed_train_step_matches_eager():

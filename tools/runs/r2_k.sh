@@ -1,0 +1,35 @@
+#!/bin/bash
+set -u
+cd "$(dirname "$0")/../.."
+mkdir -p gpurun_out
+echo "== ops + tail tests"; timeout 600 python -m pytest tests/test_ops_gpu.py tests/test_tail_gpu.py tests/test_model_gpu.py -m gpu -q -x > gpurun_out/k_ops.log 2>&1; echo "rc=$?" >> gpurun_out/k_ops.log; tail -25 gpurun_out/k_ops.log | cut -c1-300
+echo "== s2 dgrad timing"; timeout 300 python - <<'PY' 2>&1 | tail -20
+import torch, os
+from mvfnet_b200 import ops
+torch.manual_seed(0)
+def t(fn, n=10):
+    for _ in range(3): fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(n): fn()
+    e1.record(); torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / n * 1e3
+for F, C, H in [(1280, 128, 56), (1280, 256, 28), (1280, 512, 14), (96, 128, 56), (96, 512, 14)]:
+    w = torch.randn(C, C, 3, 3, device="cuda").contiguous(memory_format=torch.channels_last).requires_grad_()
+    g = torch.randn(F, C, H // 2, H // 2, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    x = torch.randn(F, C, H, H, device="cuda", dtype=torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    wb = w.detach().to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+    ours = t(lambda: ops.conv3x3s2_dgrad_raw(g, w, H, H))
+    lib = t(lambda: torch.ops.aten.convolution_backward(g, x, wb, None, [2, 2], [1, 1], [1, 1], False, [0, 0], 1, [True, False, False]))
+    a = ops.conv3x3s2_dgrad_raw(g, w, H, H).float()
+    b = torch.ops.aten.convolution_backward(g, x, wb, None, [2, 2], [1, 1], [1, 1], False, [0, 0], 1, [True, False, False])[0].float()
+    print(F, C, H, "ours %.0f us  cudnn %.0f us  rel %.2e" % (ours, lib, ((a - b).norm() / b.norm()).item()))
+PY
+echo "== bench"; timeout 1200 python bench.py --no-gpu-bar --no-other-configs > gpurun_out/k_bench.json 2> gpurun_out/k_bench.err; python - <<'PY'
+import json
+d = json.loads(open("gpurun_out/k_bench.json").read().strip().splitlines()[-1])
+print({k: d[k] for k in ("value", "ms_per_step", "e2e", "gpu_launches", "sweep", "cuda_graph_step") if k in d})
+for k, v in d["roofline_by_family"].items(): print(k, {a: (round(b, 3) if isinstance(b, float) else b) for a, b in v.items()})
+PY
+tail -5 gpurun_out/k_bench.err
