@@ -12,6 +12,12 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu")
+    # kernel A/B work: run the suite against an experimental build (tools/build_variant.py); the product itself only
+    # ever loads mvfnet_b200/libmvf_b200.so
+    alt = os.environ.get("MVFB_TEST_LIB")
+    if alt:
+        from mvfnet_b200 import _lib
+        _lib.LIB_PATH = os.path.abspath(alt)
 
 
 def pytest_collection_modifyitems(config, items):

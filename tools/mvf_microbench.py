@@ -14,6 +14,9 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
+if "--lib" in sys.argv:                                       # an experimental build (tools/build_variant.py)
+    from mvfnet_b200 import _lib as _l
+    _l.LIB_PATH = os.path.abspath(sys.argv[sys.argv.index("--lib") + 1])
 from mvfnet_b200 import MVF  # noqa: E402
 
 
@@ -25,6 +28,8 @@ def main():
     ap.add_argument("--T", default="8")
     ap.add_argument("--no-flush", action="store_true")
     ap.add_argument("--only-C", type=int, default=0, help="restrict to the slab shape with this C")
+    ap.add_argument("--lib", default=None, help="time this libmvf_b200.so instead of the in-tree one")
+    ap.add_argument("--fwd-only", action="store_true")
     args = ap.parse_args()
     peak = 6453.4
     pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -72,6 +77,9 @@ def main():
                                us_best=best, bytes=2 * E * 2, gbs=2 * E * 2 / med / 1e3, frac=2 * E * 2 / med / 1e3 / peak)
                     rows.append(row)
                     print(json.dumps(row), flush=True)
+                    if args.fwd_only:
+                        del x, g, m
+                        continue
                     y = m.fuse(x)
 
                     def bwd():
