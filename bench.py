@@ -286,6 +286,23 @@ def mvf_isolated(dev, B, peak, iters=8):
     g = torch.randn(B * T, H, H, C, device=dev).to(torch.bfloat16).permute(0, 3, 1, 2)
     E = B * T * Cs * H * H
     out = {"slab": "C=1024 14x14 Cs=128 T=8, %d clips, L2 flushed" % B}
+    # what ANY kernel moving these bytes achieves at this size, timed the same way: a plain device copy of the strided slab
+    # into a contiguous one (ATen's copy kernel; measurement only).  Launch + ramp + tail cost ~6 us per launch, so a
+    # 128 MB transfer cannot reach the 4 GB copy's rate that `peak` records (profiles/r02_mvf_fwd_ceiling_experiments.txt)
+    slab_src = x.detach()[:, :Cs]
+    slab_dst = torch.empty((B * T, H, H, Cs), dtype=torch.bfloat16, device=dev).permute(0, 3, 1, 2)
+    ts = []
+    for i in range(iters + 2):
+        flush.zero_()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        slab_dst.copy_(slab_src)
+        e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e3)
+    copy_us = sorted(ts[2:])[len(ts[2:]) // 2]
+    out["plain_copy_same_bytes"] = {"us": copy_us, "achieved": 2 * E * 2 / copy_us / 1e3, "frac": 2 * E * 2 / copy_us / 1e3 / peak,
+                                    "what": "ATen copy of the strided slab into a contiguous one (2*E*s bytes), same timing"}
     for training in (False, True):
         m = MVF(torch.nn.Identity(), T, C, alpha=0.125).to(dev).train(training)
         cfg = m._cfg()
@@ -302,7 +319,8 @@ def mvf_isolated(dev, B, peak, iters=8):
             ts.append(e0.elapsed_time(e1) * 1e3)
         us = sorted(ts[2:])[len(ts[2:]) // 2]
         key = "fwd_train" if training else "fwd_eval"
-        out[key] = {"us": us, "achieved": 2 * E * 2 / us / 1e3, "frac": 2 * E * 2 / us / 1e3 / peak}
+        out[key] = {"us": us, "achieved": 2 * E * 2 / us / 1e3, "frac": 2 * E * 2 / us / 1e3 / peak,
+                    "frac_of_plain_copy": copy_us / us}
         if training:
             y = m.fuse(x)
             mm.timing_begin()
