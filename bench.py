@@ -286,11 +286,12 @@ def mvf_isolated(dev, B, peak, iters=8):
     g = torch.randn(B * T, H, H, C, device=dev).to(torch.bfloat16).permute(0, 3, 1, 2)
     E = B * T * Cs * H * H
     out = {"slab": "C=1024 14x14 Cs=128 T=8, %d clips, L2 flushed" % B}
-    # what ANY kernel moving these bytes achieves at this size, timed the same way: a plain device copy of the strided slab
-    # into a contiguous one (ATen's copy kernel; measurement only).  Launch + ramp + tail cost ~6 us per launch, so a
-    # 128 MB transfer cannot reach the 4 GB copy's rate that `peak` records (profiles/r02_mvf_fwd_ceiling_experiments.txt)
-    slab_src = x.detach()[:, :Cs]
-    slab_dst = torch.empty((B * T, H, H, Cs), dtype=torch.bfloat16, device=dev).permute(0, 3, 1, 2)
+    # what ANY kernel moving these bytes achieves at this size, timed the same way: a plain contiguous device copy of as many
+    # bytes (ATen's copy kernel; measurement only -- tools/ubench/slab_copy.cu shows the slab's strided layout costs the
+    # same).  Launch + ramp + tail cost ~6 us per launch, so a 128 MB transfer cannot reach the 4 GB copy's rate that
+    # `peak` records (profiles/r02_mvf_fwd_ceiling_experiments.txt)
+    slab_src = torch.empty(E, dtype=torch.bfloat16, device=dev).normal_()
+    slab_dst = torch.empty_like(slab_src)
     ts = []
     for i in range(iters + 2):
         flush.zero_()
@@ -302,7 +303,7 @@ def mvf_isolated(dev, B, peak, iters=8):
         ts.append(e0.elapsed_time(e1) * 1e3)
     copy_us = sorted(ts[2:])[len(ts[2:]) // 2]
     out["plain_copy_same_bytes"] = {"us": copy_us, "achieved": 2 * E * 2 / copy_us / 1e3, "frac": 2 * E * 2 / copy_us / 1e3 / peak,
-                                    "what": "ATen copy of the strided slab into a contiguous one (2*E*s bytes), same timing"}
+                                    "what": "contiguous device-to-device copy of E*s bytes (2*E*s moved), same timing"}
     for training in (False, True):
         m = MVF(torch.nn.Identity(), T, C, alpha=0.125).to(dev).train(training)
         cfg = m._cfg()

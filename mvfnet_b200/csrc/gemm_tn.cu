@@ -59,9 +59,10 @@ struct GemmArgs {
   __nv_bfloat16* scat;
 };
 
-template <int BN>
+template <int BN, bool RES = false>
 struct Cfg {
-  static constexpr int kStages = BN >= 256 ? 3 : (BN >= 128 ? 5 : 6);
+  // RES (addend tile prefetched by TMA into two buffers of its own): fewer stages make room for them
+  static constexpr int kStages = RES ? (BN >= 128 ? 3 : 4) : (BN >= 256 ? 3 : (BN >= 128 ? 5 : 6));
   static constexpr int kABytes = BM * BK * 2;                 // 16 KB
   static constexpr int kBBytes = BN * BK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -70,29 +71,40 @@ struct Cfg {
   static constexpr int kTmemCols = 2 * BN < 32 ? 32 : 2 * BN; // power of two >= 32: BN in {64,128,256} -> 128,256,512
   static constexpr int kStatParts = kEpiThreads / (BN / 2);   // row parts of the statistics pass (BN = 256: 2, 128: 4, 64: 8)
   static constexpr int kStatBytes = kStatParts * BN * 2 * 4;  // [part][sum | sumsq][BN] fp32 = 4 KB
-  static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + kStagingBytes + 256 + kStatBytes;
+  static constexpr size_t kSmem = 1024 /*align slack*/ + (size_t)kStages * kStageBytes + kStagingBytes + 256 + kStatBytes +
+                                  (RES ? 2 * kStagingBytes : 0);
+  static_assert(kSmem <= 227 * 1024, "shared memory budget");
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int BN, bool IM2COL>
+// RES: the addend (a.res) arrives by TMA (map tmR: the output's geometry over the addend) into two shared-memory buffers,
+// requested two tiles ahead by the epilogue -- its latency never meets the epilogue.  (The first version copied the tile
+// with __ldg inside the epilogue: on the K <= 128 layers, where the epilogue IS the critical path, the fused add cost
+// as much as the separate add kernel it replaced -- profiles/r02_step_by_shape.txt.)  RES = false with a.res set is
+// that older in-epilogue copy, kept for the im2col kernels (inference only).
+template <int BN, bool IM2COL, bool RES>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
-               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD, const GemmArgs a) {
-  using C = Cfg<BN>;
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+               const __grid_constant__ CUtensorMap tmR, const GemmArgs a) {
+  using C = Cfg<BN, RES>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;                                        // kStages x [A tile | B tile]
   uint8_t* staging = smem + (size_t)C::kStages * C::kStageBytes;     // BM x BN bf16, 64-column swizzled panels
-  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + C::kStagingBytes);
+  uint8_t* addend = staging + C::kStagingBytes;                      // RES: two more tiles of the same layout
+  uint8_t* tail = addend + (RES ? 2 * C::kStagingBytes : 0);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   uint64_t* full = bars;                      // [kStages]
   uint64_t* empty = bars + C::kStages;        // [kStages]
   uint64_t* tmem_full = empty + C::kStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;       // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* s_stat = reinterpret_cast<float*>(staging + C::kStagingBytes + 256);   // [kStatParts][2][BN]
+  uint64_t* res_full = tmem_empty + 2;        // [2] (RES)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + 2);
+  float* s_stat = reinterpret_cast<float*>(tail + 256);             // [kStatParts][2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = a.K / BK;
@@ -110,7 +122,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
       mbar_init(&tmem_empty[s], kEpiThreads / 32);
+      mbar_init(&res_full[s], 1);
     }
+    if (RES) tma_prefetch_desc(&tmR);
     fence_barrier_init();
   }
   if (warp == 2) {
@@ -193,6 +207,17 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     const int half = (warp - 2) >> 2;                          // which half of the tile's columns this warp converts
     const int row = lane_grp * 32 + lane;                      // output row within the tile
     constexpr int kHalfN = BN / 2;
+    auto request_addend = [&](int tile_r, int buf) {           // one thread: the addend tile of `tile_r` -> buffer `buf`
+      const int mr = tile_r / a.n_tiles, nr = tile_r - mr * a.n_tiles;
+      mbar_arrive_expect_tx(&res_full[buf], C::kStagingBytes);
+#pragma unroll
+      for (int p = 0; p < C::kPanels; ++p)
+        tma_load_2d(addend + (size_t)buf * C::kStagingBytes + (size_t)p * (BM * 128), &tmR, &res_full[buf], nr * BN + p * 64, mr * BM);
+    };
+    if (RES && et == 0) {
+      if (blockIdx.x < total_tiles) request_addend(blockIdx.x, 0);
+      if (blockIdx.x + gridDim.x < total_tiles) request_addend(blockIdx.x + gridDim.x, 1);
+    }
     int it = 0;
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
       const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
@@ -205,7 +230,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       // warp reads whole 128- .. 512-byte rows), in the swizzled layout the results will have -- while this tile's MMAs
       // are still running.  Each thread later adds its own row chunks from shared memory (the first version read the
       // addend row-wise from global memory per thread: 32 cache lines per load instruction, 3.5 ms per step).
-      if (a.res) {
+      if (!RES && a.res) {
         constexpr int kChunksPerRow = BN / 8;                    // 16-byte chunks per tile row
         const long long m0 = (long long)mt * BM;
 #pragma unroll 4
@@ -218,7 +243,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
-      if (a.res) named_bar_sync(1, kEpiThreads);               // every addend chunk is in place
+      if (!RES && a.res) named_bar_sync(1, kEpiThreads);       // every addend chunk is in place
+      if (RES) mbar_wait(&res_full[acc], acc_ph);              // this tile's addend has landed (requested two tiles ago)
+      const uint8_t* add_tile = RES ? addend + (size_t)acc * C::kStagingBytes : staging;
       const uint32_t taddr = tmem_base + (uint32_t)(acc * BN + half * kHalfN) + ((uint32_t)(lane_grp * 32) << 16);
 #pragma unroll 1
       for (int cc = 0; cc < kHalfN; cc += 32) {
@@ -239,11 +266,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           }
         }
         uint8_t* panel = staging + (size_t)(c0 >> 6) * (BM * 128) + (size_t)row * 128;
+        const uint8_t* apanel = add_tile + (size_t)(c0 >> 6) * (BM * 128) + (size_t)row * 128;
         const int chunk0 = (c0 & 63) >> 3;
         if (a.res && nt * BN + c0 >= a.res_col0) {             // this thread's own row chunks of the staged addend
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint4 r4 = *reinterpret_cast<const uint4*>(panel + (((chunk0 + q) ^ (row & 7)) << 4));
+            const uint4 r4 = *reinterpret_cast<const uint4*>(apanel + (((chunk0 + q) ^ (row & 7)) << 4));
             const uint32_t w4[4] = {r4.x, r4.y, r4.z, r4.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -302,6 +330,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 #pragma unroll
         for (int p = 0; p < C::kPanels; ++p) tma_store_2d(&tmD, staging + (size_t)p * (BM * 128), nt * BN + p * 64, mt * BM);
         tma_store_commit();
+        // every epilogue thread has read this tile's addend (the barrier above): its buffer takes the tile after next
+        if (RES && tile + 2 * (int)gridDim.x < total_tiles) request_addend(tile + 2 * (int)gridDim.x, acc);
       }
       // per-column statistics of the rounded tile (rows beyond M were zero-filled by TMA: they add nothing).  A work
       // item is (column pair, row part): one 32-bit shared-memory load yields two columns of a row, consecutive threads
@@ -359,20 +389,20 @@ int make_2d_map(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 }
 
-template <int BN, bool IM2COL>
+template <int BN, bool IM2COL, bool RES = false>
 int launch_kernel(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmB, const CUtensorMap& tmD,
-                  GemmArgs a, cudaStream_t st) {
-  using C = Cfg<BN>;
+                  const CUtensorMap& tmR, GemmArgs a, cudaStream_t st) {
+  using C = Cfg<BN, RES>;
   a.m_tiles = (int)((a.M + BM - 1) / BM);
   a.n_tiles = a.N / BN;
   static DevOnce once;
   if (once.pending()) {
-    MVFB_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+    MVFB_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, IM2COL, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
     once.done();
   }
   int grid = a.m_tiles * a.n_tiles;
   if (grid > num_sms()) grid = num_sms();
-  gemm_tn_kernel<BN, IM2COL><<<grid, kThreads, C::kSmem, st>>>(tmA0, tmA1, tmB, tmD, a);
+  gemm_tn_kernel<BN, IM2COL, RES><<<grid, kThreads, C::kSmem, st>>>(tmA0, tmA1, tmB, tmD, tmR, a);
   count_launch();
   MVFB_LAUNCH_CHECK();
   return MVFB_OK;
@@ -385,11 +415,10 @@ struct Epi {                       // optional inference epilogue
   int res_col0 = 0;                // first column the addend applies to
 };
 
-template <int BN>
+template <int BN, bool RES = false>
 int launch(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* b, const void* res, long long ldr,
            void* out, float* colsum, float* colsq, const Epi& ep, cudaStream_t st) {
-  using C = Cfg<BN>;
-  CUtensorMap tmA0, tmA1, tmB, tmD;
+  CUtensorMap tmA0, tmA1, tmB, tmD, tmR;
   int rc;
   // A1 is addressed with the GEMM's own k coordinate, so its map spans columns [0, K) of the source rows
   if ((rc = make_2d_map(&tmA1, a1, (uint64_t)d->K, (uint64_t)d->M, (uint64_t)d->lda1, BK, BM))) return rc;
@@ -400,6 +429,8 @@ int launch(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* 
   }
   if ((rc = make_2d_map(&tmB, b, (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldb, BK, BN))) return rc;
   if ((rc = make_2d_map(&tmD, out, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldd, 64, BM))) return rc;
+  tmR = tmD;
+  if (RES && (rc = make_2d_map(&tmR, res, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)ldr, 64, BM))) return rc;
   GemmArgs a;
   a.M = d->M; a.N = d->N; a.K = d->K; a.K0 = d->K0;
   a.colsum = colsum; a.colsq = colsq;
@@ -408,7 +439,7 @@ int launch(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* 
   a.Cin = a.Ho = a.Wo = a.stride = a.pad = 0;
   a.ks = 1;
   a.scat = nullptr;
-  return launch_kernel<BN, false>(tmA0, tmA1, tmB, tmD, a, st);
+  return launch_kernel<BN, false, RES>(tmA0, tmA1, tmB, tmD, tmR, a, st);
 }
 
 // 3x3 / pad 1 convolution: A gathered by TMA im2col from x (F, H, W, Cin); B = weights (Cout, 3, 3, Cin)
@@ -435,7 +466,7 @@ int launch_conv3x3(const mvfb_conv_desc* d, const void* x, const void* w, void* 
   a.ep_scale = ep.scale; a.ep_shift = ep.shift; a.ep_relu = ep.relu;
   a.Cin = d->Cin; a.Ho = Ho; a.Wo = Wo; a.stride = d->stride; a.ks = d->ksize; a.pad = pad;
   a.scat = nullptr;
-  return launch_kernel<BN, true>(tmA, tmA, tmB, tmD, a, st);
+  return launch_kernel<BN, true>(tmA, tmA, tmB, tmD, tmD, a, st);
 }
 
 // ---- stride-2 3x3 input gradient (backbones/resnet.py:163-170 with stride 2: conv2 of the first block of layer2/3/4).
@@ -468,7 +499,7 @@ int launch_window(const void* g, int F, int Ho, int Wo, int Cout, int Cin, int k
   a.res = nullptr; a.ldr = 0; a.res_col0 = 0;
   a.ep_scale = nullptr; a.ep_shift = nullptr; a.ep_relu = 0;
   a.Cin = Cout; a.Ho = Ho; a.Wo = Wo; a.stride = 1; a.ks = kw; a.pad = 0;
-  return launch_kernel<BN, true>(tmA, tmA, tmB, tmD, a, st);
+  return launch_kernel<BN, true>(tmA, tmA, tmB, tmD, tmD, a, st);
 }
 
 }  // namespace
@@ -521,6 +552,12 @@ static int conv1x1_gemm_impl(const mvfb_gemm_desc* d, const void* a0, const void
   cudaStream_t st = (cudaStream_t)stream;
   MVFB_CHECK(!ep.scale || (ep.shift && !((uintptr_t)ep.scale & 15) && !((uintptr_t)ep.shift & 15)), MVFB_ERR_ARG,
              "the epilogue scale needs a shift, both 16-byte aligned");
+  // addend by TMA (two extra tiles of shared memory, BN <= 128, 3-4 stages) where the epilogue paces the kernel; with a
+  // long K loop the epilogue hides behind the MMAs anyway and the wider BN = 256 tile wins (layer4: K = 512)
+  if (res && (d->K <= 256 || d->N % 256 != 0)) {
+    if (d->N % 128 == 0) return launch<128, true>(d, a0, a1, b, res, ldr, out, colsum, colsq, ep, st);
+    return launch<64, true>(d, a0, a1, b, res, ldr, out, colsum, colsq, ep, st);
+  }
   if (d->N % 256 == 0) return launch<256>(d, a0, a1, b, res, ldr, out, colsum, colsq, ep, st);
   if (d->N % 128 == 0) return launch<128>(d, a0, a1, b, res, ldr, out, colsum, colsq, ep, st);
   return launch<64>(d, a0, a1, b, res, ldr, out, colsum, colsq, ep, st);
