@@ -79,7 +79,56 @@ stem_im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
 __device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// ---- packed bf16 helpers of the pooling kernels
+__device__ __forceinline__ uint32_t hmax2_nan(uint32_t a, uint32_t b) {        // NaN-propagating maximum of both halves
+  uint32_t d;
+  asm("max.NaN.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ uint32_t heq2(uint32_t a, uint32_t b) {             // 0xffff per half where a == b
+  uint32_t d;
+  asm("set.eq.u32.bf16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+  return d;
+}
+__device__ __forceinline__ bool has_nan2(uint32_t v) {                          // either half is a NaN
+  return (((v & 0x7fff7fffu) + 0x007f007fu) & 0x80008000u) != 0u;
+}
+
+// ATen's rule restated literally for a window that holds a NaN: `(val > maxval) || isnan(val)`, the first valid tap
+// replaces -inf.  Out of line and self-contained (it reloads the taps) so that the common path keeps them in registers.
+struct PoolOut { uint32_t m[4], a2[4]; };
+__device__ __noinline__ PoolOut maxpool_window_scalar(const uint4* px, int rowp, int C8, uint32_t okmask) {
+  float best[8];
+  int arg[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; arg[e] = 0; }
+  bool any = false;
+  for (int tp = 0; tp < 9; ++tp) {
+    if (!((okmask >> tp) & 1u)) continue;
+    const uint4 q4 = __ldg(px + (tp / 3) * rowp + (tp % 3) * C8);
+    const uint32_t w4[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const float lo = bf_lo(w4[q]), hi = bf_hi(w4[q]);
+      if (!any || lo > best[2 * q] || lo != lo) { best[2 * q] = lo; arg[2 * q] = tp; }
+      if (!any || hi > best[2 * q + 1] || hi != hi) { best[2 * q + 1] = hi; arg[2 * q + 1] = tp; }
+    }
+    any = true;
+  }
+  PoolOut o;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    o.m[q] = pack_bf16(best[2 * q], best[2 * q + 1]);
+    o.a2[q] = (uint32_t)arg[2 * q] | ((uint32_t)arg[2 * q + 1] << 16);
+  }
+  return o;
+}
+
 // x: (F, H, W, C) bf16 NHWC -> y: (F, Ho, Wo, C), idx: (F, Ho, Wo, C) bytes.  One thread per (output pixel, 8 channels).
+// The maximum is taken on packed bf16 pairs (3-input VHMNMX), the arg-max is the FIRST tap in scan order equal to it
+// (ATen's `val > maxval` rule: ties keep the earlier tap); a window that holds a NaN takes the scalar path above.  The nine
+// taps sit at fixed offsets from one 64-bit pointer per thread (first version: 450 instructions per thread, a third of them
+// 64-bit index arithmetic and per-channel compares; 74 % issue-bound -- profiles/r02_stem_pool_ncu.txt).
 template <typename I>
 __global__ void __launch_bounds__(256)
 maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint2* __restrict__ idx, int H, int W, int Ho,
@@ -91,42 +140,58 @@ maxpool_fwd_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, uint2* __
   const int ow = (int)(t % (I)Wo); t /= (I)Wo;
   const int oh = (int)(t % (I)Ho);
   const long long f = (long long)(t / (I)Ho);
-  float best[8];
-  int arg[8];
-#pragma unroll
-  for (int e = 0; e < 8; ++e) { best[e] = -INFINITY; arg[e] = 0; }
-  bool any = false;
+  const int ih0 = 2 * oh - 1, iw0 = 2 * ow - 1;
+  const uint4* px = x + ((f * H + ih0) * W + iw0) * C8 + c8;    // tap (0, 0); only dereferenced where it is inside the image
+  const int rowp = W * C8;
+  uint32_t okmask = 0;
+  uint32_t v[9][4];
 #pragma unroll
   for (int kh = 0; kh < 3; ++kh) {
-    const int ih = 2 * oh - 1 + kh;
-    if (ih < 0 || ih >= H) continue;
 #pragma unroll
     for (int kw = 0; kw < 3; ++kw) {
-      const int iw = 2 * ow - 1 + kw;
-      if (iw < 0 || iw >= W) continue;
-      const uint4 v = __ldg(x + ((f * H + ih) * W + iw) * C8 + c8);
-      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float lo = bf_lo(w4[q]), hi = bf_hi(w4[q]);
-        // ATen: (val > maxval) || isnan(val); the first valid element always replaces -inf
-        if (!any || lo > best[2 * q] || lo != lo) { best[2 * q] = lo; arg[2 * q] = kh * 3 + kw; }
-        if (!any || hi > best[2 * q + 1] || hi != hi) { best[2 * q + 1] = hi; arg[2 * q + 1] = kh * 3 + kw; }
-      }
-      any = true;
+      const int tp = kh * 3 + kw;
+      const bool ok = (unsigned)(ih0 + kh) < (unsigned)H && (unsigned)(iw0 + kw) < (unsigned)W;
+      uint4 q = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);   // -inf: never wins
+      if (ok) { q = __ldg(px + kh * rowp + kw * C8); okmask |= 1u << tp; }
+      v[tp][0] = q.x; v[tp][1] = q.y; v[tp][2] = q.z; v[tp][3] = q.w;
     }
   }
-  uint4 o;
-  o.x = pack_bf16(best[0], best[1]); o.y = pack_bf16(best[2], best[3]);
-  o.z = pack_bf16(best[4], best[5]); o.w = pack_bf16(best[6], best[7]);
-  y[i] = o;
-  uint2 k;
-  k.x = arg[0] | (arg[1] << 8) | (arg[2] << 16) | (arg[3] << 24);
-  k.y = arg[4] | (arg[5] << 8) | (arg[6] << 16) | (arg[7] << 24);
+  uint32_t m[4], a2[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    m[q] = v[0][q];
+#pragma unroll
+    for (int tp = 1; tp < 9; ++tp) m[q] = hmax2_nan(m[q], v[tp][q]);
+  }
+  // Scan from the last tap to the first, so that the earliest tap equal to the maximum is the one written last; padded
+  // taps (-inf) are masked out, and tap (1, 1) -- inside the image for every window -- is the default.
+#pragma unroll
+  for (int q = 0; q < 4; ++q) a2[q] = 0x00040004u;
+#pragma unroll
+  for (int tp = 8; tp >= 0; --tp) {
+    const uint32_t on = (okmask >> tp) & 1u ? 0xffffffffu : 0u;
+    const uint32_t code = (uint32_t)tp * 0x00010001u;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t e = heq2(v[tp][q], m[q]) & on;
+      a2[q] = (e & code) | (~e & a2[q]);
+    }
+  }
+  if (has_nan2(m[0]) || has_nan2(m[1]) || has_nan2(m[2]) || has_nan2(m[3])) {
+    const PoolOut o = maxpool_window_scalar(px, rowp, C8, okmask);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { m[q] = o.m[q]; a2[q] = o.a2[q]; }
+  }
+  y[i] = make_uint4(m[0], m[1], m[2], m[3]);
+  uint2 k;                                                       // bytes 0 and 2 of each pair register
+  k.x = __byte_perm(a2[0], a2[1], 0x6420);
+  k.y = __byte_perm(a2[2], a2[3], 0x6420);
   idx[i] = k;
 }
 
 // dx[f, ih, iw, c] = sum over the windows (oh, ow) that contain (ih, iw) of g[f, oh, ow, c] * [idx[f, oh, ow, c] == position]
+// (fp32 sum of up to four bf16 terms, rounded once).  The byte compare and the masking are SIMD-in-register; the masked
+// bf16 pairs are accumulated by the mixed-precision FMA (x * 1.0 + acc).
 template <typename I>
 __global__ void __launch_bounds__(256)
 maxpool_bwd_kernel(const uint4* __restrict__ g, const uint2* __restrict__ idx, uint4* __restrict__ dx, int H, int W,
@@ -144,35 +209,128 @@ maxpool_bwd_kernel(const uint4* __restrict__ g, const uint2* __restrict__ idx, u
   // windows: 2*oh - 1 <= ih <= 2*oh + 1
   const int oh0 = ih >> 1, oh1 = (ih + 1) >> 1;                 // equal when ih is even ... (ih odd: two windows)
   const int ow0 = iw >> 1, ow1 = (iw + 1) >> 1;
+  uint2 kk[4];
+  uint4 vv[4];
+  int pos[4];
 #pragma unroll
   for (int a = 0; a < 2; ++a) {
     const int oh = a == 0 ? oh0 : oh1;
-    if (a == 1 && oh1 == oh0) continue;
-    if (oh >= Ho) continue;
-    const int kh = ih - (2 * oh - 1);
 #pragma unroll
     for (int b = 0; b < 2; ++b) {
       const int ow = b == 0 ? ow0 : ow1;
-      if (b == 1 && ow1 == ow0) continue;
-      if (ow >= Wo) continue;
-      const int pos = kh * 3 + (iw - (2 * ow - 1));
-      const long long o = ((f * Ho + oh) * Wo + ow) * C8 + c8;
-      const uint2 k = __ldg(idx + o);
-      const uint4 v = __ldg(g + o);
-      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const uint32_t kk = q < 2 ? k.x : k.y;
-        const int sh = (q & 1) * 16;
-        if ((int)((kk >> sh) & 0xff) == pos) acc[2 * q] += bf_lo(w4[q]);
-        if ((int)((kk >> (sh + 8)) & 0xff) == pos) acc[2 * q + 1] += bf_hi(w4[q]);
+      const int w = a * 2 + b;
+      const bool on = !(a == 1 && oh1 == oh0) && oh < Ho && !(b == 1 && ow1 == ow0) && ow < Wo;
+      pos[w] = on ? (ih - (2 * oh - 1)) * 3 + (iw - (2 * ow - 1)) : 0xff;     // 0xff matches no recorded position
+      kk[w] = make_uint2(0u, 0u);
+      vv[w] = make_uint4(0u, 0u, 0u, 0u);
+      if (on) {
+        const long long o = ((f * Ho + oh) * Wo + ow) * C8 + c8;
+        kk[w] = __ldg(idx + o);
+        vv[w] = __ldg(g + o);
       }
+    }
+  }
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    const uint32_t p4 = (uint32_t)pos[w] * 0x01010101u;
+    const uint32_t e0 = __vcmpeq4(kk[w].x, p4), e1 = __vcmpeq4(kk[w].y, p4);   // 0xff per matching byte
+    const uint32_t w4[4] = {vv[w].x & __byte_perm(e0, 0u, 0x1100), vv[w].y & __byte_perm(e0, 0u, 0x3322),
+                            vv[w].z & __byte_perm(e1, 0u, 0x1100), vv[w].w & __byte_perm(e1, 0u, 0x3322)};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      asm("{\n\t.reg .b16 lo, hi, one;\n\t"
+          "mov.b32 {lo, hi}, %2;\n\t"
+          "mov.b16 one, 0x3f80;\n\t"
+          "fma.rn.f32.bf16 %0, lo, one, %0;\n\t"
+          "fma.rn.f32.bf16 %1, hi, one, %1;\n\t}"
+          : "+f"(acc[2 * q]), "+f"(acc[2 * q + 1])
+          : "r"(w4[q]));
     }
   }
   uint4 o;
   o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
   o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
   dx[i] = o;
+}
+
+// Even H and W (the stem: 112 x 112): one thread per 2 x 2 block of input pixels and 8 channels.  The block (2a.., 2b..) is
+// covered by the four windows (a | a+1, b | b+1) only, and every (pixel, window) pair has a FIXED tap position:
+//   (2a, 2b): window (a, b) tap 4                       (2a, 2b+1): (a, b) tap 5, (a, b+1) tap 3
+//   (2a+1, 2b): (a, b) tap 7, (a+1, b) tap 1            (2a+1, 2b+1): (a, b) 8, (a, b+1) 6, (a+1, b) 2, (a+1, b+1) 0
+// so four (g, idx) loads serve four pixels (the per-pixel kernel above loads nine) and the position compares are against
+// constants.  byte == tap  <=>  ((byte ^ tap) + 0x7f) has its top bit clear (bytes are < 16); PRMT's sign-replicate mode
+// spreads that bit over the bf16 half it guards.
+// PRMT in its generic PTX form: selector nibbles 8..11 replicate the SIGN of source byte 0..3 over the target byte
+// (CUDA's __byte_perm masks the selector to three bits and cannot express this)
+__device__ __forceinline__ uint32_t prmt_sign(uint32_t a, uint32_t sel) {
+  uint32_t d;
+  asm("prmt.b32 %0, %1, %1, %2;" : "=r"(d) : "r"(a), "r"(sel));
+  return d;
+}
+__device__ __forceinline__ void pool_take(float (&acc)[8], const uint4& gv, const uint2& kv, uint32_t tap) {
+  const uint32_t p4 = tap * 0x01010101u;
+  const uint32_t n0 = (kv.x ^ p4) + 0x7f7f7f7fu, n1 = (kv.y ^ p4) + 0x7f7f7f7fu;      // top bit of a byte set <=> not this tap
+  const uint32_t w4[4] = {gv.x & ~prmt_sign(n0, 0x9988u), gv.y & ~prmt_sign(n0, 0xbbaau),
+                          gv.z & ~prmt_sign(n1, 0x9988u), gv.w & ~prmt_sign(n1, 0xbbaau)};
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    asm("{\n\t.reg .b16 lo, hi, one;\n\t"
+        "mov.b32 {lo, hi}, %2;\n\t"
+        "mov.b16 one, 0x3f80;\n\t"
+        "fma.rn.f32.bf16 %0, lo, one, %0;\n\t"
+        "fma.rn.f32.bf16 %1, hi, one, %1;\n\t}"
+        : "+f"(acc[2 * q]), "+f"(acc[2 * q + 1])
+        : "r"(w4[q]));
+  }
+}
+__device__ __forceinline__ uint4 pool_pack(const float (&acc)[8]) {
+  uint4 o;
+  o.x = pack_bf16(acc[0], acc[1]); o.y = pack_bf16(acc[2], acc[3]);
+  o.z = pack_bf16(acc[4], acc[5]); o.w = pack_bf16(acc[6], acc[7]);
+  return o;
+}
+
+template <typename I>
+__global__ void __launch_bounds__(256)
+maxpool_bwd_block_kernel(const uint4* __restrict__ g, const uint2* __restrict__ idx, uint4* __restrict__ dx, int W, int Ho, int Wo,
+                         int C8, long long total) {
+  const I i = (I)blockIdx.x * (I)blockDim.x + threadIdx.x;       // (f, a, b, c8): the layout of g itself
+  if ((long long)i >= total) return;
+  const int c8 = (int)(i % (I)C8);
+  I t = i / (I)C8;
+  const int b = (int)(t % (I)Wo); t /= (I)Wo;
+  const int a = (int)(t % (I)Ho);
+  const long long f = (long long)(t / (I)Ho);
+  const bool right = b + 1 < Wo, down = a + 1 < Ho;
+  const int rowo = Wo * C8;
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+  const uint2 k9 = make_uint2(0x09090909u, 0x09090909u);          // tap 9 does not exist: matches nothing
+  const uint4 g00 = __ldg(g + i);
+  const uint2 k00 = __ldg(idx + i);
+  const uint4 g01 = right ? __ldg(g + i + C8) : z4;
+  const uint2 k01 = right ? __ldg(idx + i + C8) : k9;
+  const uint4 g10 = down ? __ldg(g + i + rowo) : z4;
+  const uint2 k10 = down ? __ldg(idx + i + rowo) : k9;
+  const uint4 g11 = (right && down) ? __ldg(g + i + rowo + C8) : z4;
+  const uint2 k11 = (right && down) ? __ldg(idx + i + rowo + C8) : k9;
+  uint4* out = dx + ((f * (2 * Ho) + 2 * a) * (long long)W + 2 * b) * C8 + c8;
+  float acc[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  pool_take(acc, g00, k00, 4u);
+  out[0] = pool_pack(acc);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  pool_take(acc, g00, k00, 5u); pool_take(acc, g01, k01, 3u);
+  out[C8] = pool_pack(acc);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  pool_take(acc, g00, k00, 7u); pool_take(acc, g10, k10, 1u);
+  out[(long long)W * C8] = pool_pack(acc);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+  pool_take(acc, g00, k00, 8u); pool_take(acc, g01, k01, 6u); pool_take(acc, g10, k10, 2u); pool_take(acc, g11, k11, 0u);
+  out[(long long)W * C8 + C8] = pool_pack(acc);
 }
 
 }  // namespace
@@ -222,6 +380,18 @@ int maxpool3x3s2_bwd(const void* g, const void* idx, void* dx, long long F, int 
   MVFB_CHECK(!((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(dx)) & 15) && !(reinterpret_cast<uintptr_t>(idx) & 7),
              MVFB_ERR_ARG, "maxpool3x3s2_bwd: misaligned tensors");
   const int Ho = (H + 2 - 3) / 2 + 1, Wo = (W + 2 - 3) / 2 + 1;
+  if (H % 2 == 0 && W % 2 == 0) {                                // 2 x 2 input block per thread
+    const long long blocks4 = F * Ho * Wo * (C / 8);
+    if (blocks4 < (1LL << 31))
+      maxpool_bwd_block_kernel<uint32_t><<<(unsigned)ceil_div_ll(blocks4, 256), 256, 0, (cudaStream_t)stream>>>(
+          (const uint4*)g, (const uint2*)idx, (uint4*)dx, W, Ho, Wo, C / 8, blocks4);
+    else
+      maxpool_bwd_block_kernel<long long><<<(unsigned)ceil_div_ll(blocks4, 256), 256, 0, (cudaStream_t)stream>>>(
+          (const uint4*)g, (const uint2*)idx, (uint4*)dx, W, Ho, Wo, C / 8, blocks4);
+    count_launch();
+    MVFB_LAUNCH_CHECK();
+    return MVFB_OK;
+  }
   const long long total = F * H * W * (C / 8);
   if (total < (1LL << 31))
     maxpool_bwd_kernel<uint32_t><<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(

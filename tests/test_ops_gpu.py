@@ -280,7 +280,29 @@ def test_maxpool3x3s2_vs_torch(F, C, H, W):
     assert torch.equal(xa.grad, xb.grad)
 
 
-@pytest.mark.parametrize("M,N,K", [(300, 64, 64), (12544, 256, 64), (1000, 128, 256)])
+def test_maxpool3x3s2_negative_values_and_nans():
+    """Signed inputs (the packed maximum must order negatives correctly) with a few NaNs: ATen's rule `(val > maxval) ||
+    isnan(val)` makes a NaN win its windows and the LAST NaN of a window take the gradient."""
+    from mvfnet_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    x = torch.randn((3, 64, 30, 30), generator=g)
+    x.view(-1)[torch.randint(0, x.numel(), (200,), generator=g)] = float("nan")
+    x = x.cuda().bfloat16().contiguous(memory_format=torch.channels_last)
+    pool = torch.nn.MaxPool2d(3, 2, 1)
+    xa = x.clone().requires_grad_(True)
+    xb = x.clone().requires_grad_(True)
+    ya = ops.maxpool3x3s2(xa)
+    yb = pool(xb)
+    assert torch.equal(torch.isnan(ya), torch.isnan(yb)) and torch.isnan(yb).any()
+    assert torch.equal(torch.nan_to_num(ya.float(), nan=7.0), torch.nan_to_num(yb.float(), nan=7.0))
+    gy = torch.randn(yb.shape, generator=g).cuda().bfloat16().contiguous(memory_format=torch.channels_last)
+    ya.backward(gy)
+    yb.backward(gy)
+    assert torch.equal(xa.grad, xb.grad)
+
+
+@pytest.mark.parametrize("M,N,K", [(300, 64, 64), (12544, 256, 64), (1000, 128, 256), (100000, 256, 64), (70001, 192, 128),
+                                   (50000, 512, 512)])
 def test_gemm_add_epilogue(M, N, K):
     """conv1x1_gemm_add: out = A B^T + addend (the fused gradient sum at a Bottleneck's input), M tail included."""
     from mvfnet_b200 import ops
@@ -293,3 +315,42 @@ def test_gemm_add_epilogue(M, N, K):
     assert (out.float() - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
     plain, _, _ = ops.gemm_tn(a, b)
     assert not torch.equal(out, plain)
+
+
+@pytest.mark.parametrize("M,N,K,col0", [(70001, 256, 64, 32), (30000, 1024, 256, 128), (9000, 2048, 512, 256)])
+def test_gemm_add_cols_epilogue(M, N, K, col0):
+    """conv1x1_gemm_add_cols: the addend applies to columns >= col0 only (MVF blocks: the slab's gradient arrives through
+    mvf_bwd_add); many tiles per CTA so the two addend buffers of the TMA-prefetch path cycle."""
+    from mvfnet_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K + col0)
+    a = torch.randn((M, K), generator=g).cuda().bfloat16()
+    b = (torch.randn((N, K), generator=g) * 0.1).cuda().bfloat16()
+    r = torch.randn((M, N), generator=g).cuda().bfloat16()
+    out, _, _ = ops.gemm_tn(a, b, add=r, add_col0=col0)
+    ref = a.float() @ b.float().t()
+    ref[:, col0:] += r.float()[:, col0:]
+    assert (out.float() - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
+
+
+@pytest.mark.parametrize("M,N,K,relu", [(50000, 256, 64, True), (20000, 512, 128, True), (20000, 1024, 256, False),
+                                        (6000, 2048, 512, True)])
+def test_gemm_bnact_residual_epilogue(M, N, K, relu):
+    """conv1x1_gemm_bnact: out = [relu]((A B^T) * scale + shift + res) -- conv3 + eval bn3 + identity + ReLU of the
+    inference path, against fp32 torch."""
+    from mvfnet_b200 import ops
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn((M, K), generator=g).cuda().bfloat16()
+    b = (torch.randn((N, K), generator=g) * 0.1).cuda().bfloat16()
+    r = torch.randn((M, N), generator=g).cuda().bfloat16()
+    scale = (0.5 + torch.rand(N, generator=g)).cuda()
+    shift = torch.randn(N, generator=g).cuda()
+    out = ops.gemm_bnact(a, b, scale, shift, relu, res=r)
+    ref = (a.float() @ b.float().t()) * scale + shift + r.float()
+    if relu:
+        ref = ref.clamp_min(0)
+    assert (out.float() - ref).abs().max().item() < 1e-2 * ref.abs().max().item()
+    nores = ops.gemm_bnact(a, b, scale, shift, relu)
+    ref2 = (a.float() @ b.float().t()) * scale + shift
+    if relu:
+        ref2 = ref2.clamp_min(0)
+    assert (nores.float() - ref2).abs().max().item() < 1e-2 * ref2.abs().max().item()
