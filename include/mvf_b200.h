@@ -217,6 +217,11 @@ int conv3x3_gemm_bnact(const mvfb_conv_desc* d, const void* x, const void* w, co
  * it. */
 int conv3x3s2_dgrad(const mvfb_conv_desc* d, const void* g, const void* wq, void* dx, mvfb_stream_t stream);
 
+/* Input gradient of the STRIDE-2 1x1 (down-sampling) convolution: g (F, H/2, W/2, Cout), wT = W^T (Cin, Cout), dx
+ * (F, H, W, Cin), bf16 NHWC, H and W even.  The GEMM dY W writes each row to pixel (2i, 2j) of dx and zeroes the three other
+ * pixels of that 2 x 2 cell: dx is written completely, no memset, no scatter pass. */
+int conv1x1s2_dgrad(const mvfb_conv_desc* d, const void* g, const void* wT, void* dx, mvfb_stream_t stream);
+
 /* Its weight gradient: dw[n, r, s, c] = sum_{f,ho,wo} g[f, ho, wo, n] * x[f, ho*stride + r - 1, wo*stride + s - 1, c]
  * (g bf16 (F, Ho, Wo, Cout); dw fp32 (Cout, 3, 3, Cin), zeroed by the call; MN-major MMA operands, the x operand
  * gathered by TMA im2col, split-K fp32 atomics over the pixel axis). */

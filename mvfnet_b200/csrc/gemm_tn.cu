@@ -57,6 +57,7 @@ struct GemmArgs {
   // scattered store (stride-2 input gradient): tile row m = (f, i, j) of the (Ho, Wo) grid goes to pixel (2i, 2j) of the
   // (2Ho, 2Wo) image `scat` points into (the parity's (ph, pw) offset is already in the pointer); null = TMA store to tmD
   __nv_bfloat16* scat;
+  int scat_fill;                   // 1: also zero the three other pixels of the row's 2 x 2 cell
 };
 
 template <int BN, bool RES = false>
@@ -295,7 +296,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           *reinterpret_cast<uint4*>(panel + (((chunk0 + q) ^ (row & 7)) << 4)) = o;
         }
       }
-      if (IM2COL && a.scat && et < BM) {                       // destination of tile row `et` (M < 2^31: checked by the host)
+      if (a.scat && et < BM) {                                 // destination of tile row `et` (M < 2^31: checked by the host)
         const unsigned m = (unsigned)mt * BM + et;
         long long off = -1;
         if (m < (unsigned)a.M) {
@@ -311,11 +312,13 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       fence_proxy_async_smem();                                // staging writes -> visible to the TMA engine
       named_bar_sync(1, kEpiThreads);
-      if (IM2COL && a.scat) {
+      if (a.scat) {
         // every output row is a pixel of its own in the double-resolution image: 16-byte chunks, a warp covers whole rows
-        // (row offsets were computed once per tile, before the barrier above: s_rowoff)
+        // (row offsets were computed once per tile, before the barrier above: s_rowoff).  scat_fill: the row owns its
+        // whole 2 x 2 cell and zeroes the other three pixels (stride-2 1x1 input gradient: dx needs no memset).
         constexpr int kChunksPerRow = BN / 8;
         const long long* s_rowoff = reinterpret_cast<const long long*>(s_stat);
+        const long long right = a.N, down = 2ll * a.Wo * a.N;      // one pixel to the right / one image row down, in elements
 #pragma unroll 4
         for (int idx = et; idx < BM * kChunksPerRow; idx += kEpiThreads) {
           const int r = idx / kChunksPerRow, ch = idx - r * kChunksPerRow;
@@ -323,7 +326,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (off >= 0) {
             const uint4 v4 = *reinterpret_cast<const uint4*>(staging + (size_t)(ch >> 3) * (BM * 128) + (size_t)r * 128 +
                                                              (((ch & 7) ^ (r & 7)) << 4));
-            *reinterpret_cast<uint4*>(a.scat + off + nt * BN + ch * 8) = v4;
+            __nv_bfloat16* dst = a.scat + off + nt * BN + ch * 8;
+            *reinterpret_cast<uint4*>(dst) = v4;
+            if (a.scat_fill) {
+              const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+              *reinterpret_cast<uint4*>(dst + right) = z4;
+              *reinterpret_cast<uint4*>(dst + down) = z4;
+              *reinterpret_cast<uint4*>(dst + down + right) = z4;
+            }
           }
         }
       } else if (et == 0) {
@@ -438,7 +448,7 @@ int launch(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* 
   a.ep_scale = ep.scale; a.ep_shift = ep.shift; a.ep_relu = ep.relu;
   a.Cin = a.Ho = a.Wo = a.stride = a.pad = 0;
   a.ks = 1;
-  a.scat = nullptr;
+  a.scat = nullptr; a.scat_fill = 0;
   return launch_kernel<BN, false, RES>(tmA0, tmA1, tmB, tmD, tmR, a, st);
 }
 
@@ -465,7 +475,7 @@ int launch_conv3x3(const mvfb_conv_desc* d, const void* x, const void* w, void* 
   a.res = (const __nv_bfloat16*)res; a.ldr = d->Cout; a.res_col0 = 0;
   a.ep_scale = ep.scale; a.ep_shift = ep.shift; a.ep_relu = ep.relu;
   a.Cin = d->Cin; a.Ho = Ho; a.Wo = Wo; a.stride = d->stride; a.ks = d->ksize; a.pad = pad;
-  a.scat = nullptr;
+  a.scat = nullptr; a.scat_fill = 0;
   return launch_kernel<BN, true>(tmA, tmA, tmB, tmD, tmD, a, st);
 }
 
@@ -493,7 +503,7 @@ int launch_window(const void* g, int F, int Ho, int Wo, int Cout, int Cin, int k
   if ((rc = make_2d_map(&tmB, wq, (uint64_t)taps * Cout, (uint64_t)Cin, (uint64_t)taps * Cout, BK, BN))) return rc;
   tmD = tmB;                                                   // unused: the epilogue scatters the rows itself
   GemmArgs a;
-  a.scat = (__nv_bfloat16*)out;
+  a.scat = (__nv_bfloat16*)out; a.scat_fill = 0;
   a.M = M; a.N = Cin; a.K = taps * Cout; a.K0 = 0;
   a.colsum = nullptr; a.colsq = nullptr;
   a.res = nullptr; a.ldr = 0; a.res_col0 = 0;
@@ -507,6 +517,41 @@ int launch_window(const void* g, int F, int Ho, int Wo, int Cout, int Cin, int k
 }  // namespace mvfb
 
 using namespace mvfb;
+
+// ---- stride-2 1x1 input gradient (the down-sampling convolution, make_res_layer resnet.py:299-303): the plain GEMM
+// dY W on the compact gradient whose rows land on the even pixels of dx; the epilogue zeroes the rest of each 2 x 2 cell.
+template <int BN>
+static int launch_s2_1x1(const mvfb_conv_desc* d, const void* g, const void* wT, void* dx, cudaStream_t st) {
+  const int Ho = d->H / 2, Wo = d->W / 2;
+  const long long M = (long long)d->F * Ho * Wo;
+  CUtensorMap tmA, tmB;
+  int rc;
+  if ((rc = make_2d_map(&tmA, g, (uint64_t)d->Cout, (uint64_t)M, (uint64_t)d->Cout, BK, BM))) return rc;
+  if ((rc = make_2d_map(&tmB, wT, (uint64_t)d->Cout, (uint64_t)d->Cin, (uint64_t)d->Cout, BK, BN))) return rc;
+  GemmArgs a;
+  a.M = M; a.N = d->Cin; a.K = d->Cout; a.K0 = 0;
+  a.colsum = nullptr; a.colsq = nullptr;
+  a.res = nullptr; a.ldr = 0; a.res_col0 = 0;
+  a.ep_scale = nullptr; a.ep_shift = nullptr; a.ep_relu = 0;
+  a.Cin = 0; a.Ho = Ho; a.Wo = Wo; a.stride = 1; a.ks = 1; a.pad = 0;
+  a.scat = (__nv_bfloat16*)dx; a.scat_fill = 1;
+  return launch_kernel<BN, false>(tmA, tmA, tmB, tmB, tmB, a, st);
+}
+
+extern "C" int conv1x1s2_dgrad(const mvfb_conv_desc* d, const void* g, const void* wT, void* dx, mvfb_stream_t stream) {
+  MVFB_CHECK(d && g && wT && dx, MVFB_ERR_ARG, "null descriptor / operand");
+  MVFB_CHECK(d->F > 0 && d->H > 0 && d->W > 0 && d->stride == 2 && d->ksize == 1 && d->H % 2 == 0 && d->W % 2 == 0,
+             MVFB_ERR_UNSUPPORTED, "conv1x1s2_dgrad takes the 1x1 stride-2 layers with even H, W (F=%d H=%d W=%d)", d->F, d->H, d->W);
+  MVFB_CHECK(d->Cin % 64 == 0 && d->Cout % BK == 0, MVFB_ERR_UNSUPPORTED, "Cin=%d and Cout=%d must be multiples of 64",
+             d->Cin, d->Cout);
+  MVFB_CHECK(!((uintptr_t)g & 15) && !((uintptr_t)wT & 15) && !((uintptr_t)dx & 15), MVFB_ERR_UNSUPPORTED,
+             "operands must be 16-byte aligned");
+  MVFB_CHECK((long long)d->F * d->H * d->W < (1ll << 31), MVFB_ERR_UNSUPPORTED, "F*H*W must stay below 2^31 pixels");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (d->Cin % 256 == 0) return launch_s2_1x1<256>(d, g, wT, dx, st);
+  if (d->Cin % 128 == 0) return launch_s2_1x1<128>(d, g, wT, dx, st);
+  return launch_s2_1x1<64>(d, g, wT, dx, st);
+}
 
 extern "C" int conv3x3s2_dgrad(const mvfb_conv_desc* d, const void* g, const void* wq, void* dx, mvfb_stream_t stream) {
   MVFB_CHECK(d && g && wq && dx, MVFB_ERR_ARG, "null descriptor / operand");

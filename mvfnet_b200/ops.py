@@ -69,6 +69,8 @@ def _L():
         L.conv3x3_gemm_bnact.argtypes = [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP, _VP, C.c_int, _VP, _VP]
         L.conv1x1_gemm_add_cols.restype = C.c_int
         L.conv1x1_gemm_add_cols.argtypes = [C.POINTER(GemmDesc), _VP, _VP, _VP, _VP, _LL, C.c_int, _VP, _VP]
+        L.conv1x1s2_dgrad.restype = C.c_int
+        L.conv1x1s2_dgrad.argtypes = [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP]
         L.conv3x3s2_dgrad.restype = C.c_int
         L.conv3x3s2_dgrad.argtypes = [C.POINTER(ConvDesc), _VP, _VP, _VP, _VP]
         L.conv1x1_gemm_add.restype = C.c_int
@@ -684,9 +686,19 @@ class _Conv1x1Strided(torch.autograd.Function):
         g = g.contiguous(memory_format=torch.channels_last)
         dx = dw = None
         if ctx.needs_input_grad[0]:
-            dxc, _, _ = gemm_tn(_rows(g), _wform(ctx.weight, "rowsT"))               # (F*Ho*Wo, Cin)
-            dx = torch.zeros((f, h, w, cin), dtype=torch.bfloat16, device=x.device)
-            dx[:, ::st, ::st, :] = dxc.view(f, g.shape[2], g.shape[3], cin)
+            cout = wb.shape[0]
+            if st == 2 and h % 2 == 0 and w % 2 == 0 and cin % 64 == 0 and cout % 64 == 0 and s2_dgrad_enabled():
+                # the GEMM's epilogue scatters its rows to the even pixels and zeroes the rest of each 2 x 2 cell
+                d = ConvDesc()
+                d.F, d.H, d.W, d.Cin, d.Cout, d.stride, d.ksize = f, h, w, cin, cout, 2, 1
+                dx = torch.empty((f, h, w, cin), dtype=torch.bfloat16, device=x.device)
+                with _T("gemm1x1", nbytes=2 * (g.numel() + dx.numel() + cin * cout), flops=2 * g.numel() * cin):
+                    rc = _L().conv1x1s2_dgrad(C.byref(d), ptr(g), ptr(_wform(ctx.weight, "rowsT")), ptr(dx), _stream())
+                _lib.check(rc, "conv1x1s2_dgrad")
+            else:
+                dxc, _, _ = gemm_tn(_rows(g), _wform(ctx.weight, "rowsT"))           # (F*Ho*Wo, Cin)
+                dx = torch.zeros((f, h, w, cin), dtype=torch.bfloat16, device=x.device)
+                dx[:, ::st, ::st, :] = dxc.view(f, g.shape[2], g.shape[3], cin)
             dx = dx.permute(0, 3, 1, 2)
         if ctx.needs_input_grad[1]:
             sink = _grad_sink(ctx.weight, (wb.shape[0], cin))
