@@ -546,6 +546,12 @@ def run_ours(args):
     timing = mvf_mod.timing_end()
     clocks = sampler.stop() if rank == 0 else None
     value = world * B * args.steps / (ms / 1e3)
+    # the timed steps must have been real training steps: a finite cross-entropy near ln(400) on random labels, a finite
+    # gradient norm (a wrong BatchNorm statistic or a skipped kernel shows up here as inf / nan / 1e7)
+    loss_check = float(train_step(dev_img[0], dev_lbl[0]).float().item())
+    gnorm_check = float(opt.grad_norm.item())
+    if not (0.0 < loss_check < 30.0) or not (0.0 < gnorm_check < 1e6):
+        raise SystemExit("bench.py: the training step is numerically broken (loss %r, grad norm %r)" % (loss_check, gnorm_check))
 
     if args.kernels_only:
         if rank == 0:
@@ -727,7 +733,8 @@ def run_ours(args):
                        "peak_hbm_gb": peak_gb},
             "e2e": {"value": e2e_value, "unit": "clips/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "ms_per_step": ms_e2e / args.steps},
-            "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "roofline_by_family": by_family,
+            "gpu_launches": int(launches), "sanity": {"loss_after_timed_steps": loss_check, "grad_norm": gnorm_check},
+            "clocks": clocks, "roofline": roofline, "roofline_by_family": by_family,
             "sweep": sweep}
     if graphed is not None:
         line["cuda_graph_step"] = dict(graphed, how="the identical step (uint8 frames -> loss -> backward -> clip -> SGD) captured once, "

@@ -256,7 +256,8 @@ class MVF(nn.Module):
 
     def _count_batch(self, cfg):
         if cfg.use_hs and cfg.training and self.bn.track_running_stats:
-            self.bn.num_batches_tracked += 1
+            from . import ops
+            ops.count_batch(self.bn)
 
     def fuse(self, x):
         """x' of MVF.py:137 (the tensor handed to self.net)."""

@@ -123,8 +123,63 @@ def register_grad_sinks(params, views):
 
 
 def new_backward_pass():
+    """Start of a training step (FlatGrads.zero_()): gradient sinks may be written again, the statistics arena is zeroed
+    by ONE fill and handed out from its start, BatchNorm step counters deferred by the previous step are applied."""
     global _SINK_STEP
     _SINK_STEP += 1
+    flush_counters()
+    for a in _STAT_ARENAS.values():
+        a[0].zero_()
+        a[1], a[2] = 0, _SINK_STEP
+
+
+# Per-column (sum, sum of squares) accumulators of the GEMM epilogues: 53 tiny zero-fills per step when allocated one by
+# one.  Inside a step protocol (new_backward_pass() at every zero_grad) they are slices of one arena zeroed once.
+_STAT_ARENAS = {}         # device -> [fp32 arena, next free element, step it was zeroed for]
+_STAT_ARENA_ELEMS = 1 << 18
+
+
+def _stat_sums(n, device):
+    """A zeroed (2, n) fp32 tensor."""
+    a = _STAT_ARENAS.get(device)
+    if a is None:
+        if _SINK_STEP == 0:                                      # nobody drives a step protocol: plain allocation
+            return torch.zeros((2, n), dtype=torch.float32, device=device)
+        a = _STAT_ARENAS[device] = [torch.zeros(_STAT_ARENA_ELEMS, dtype=torch.float32, device=device), 0, _SINK_STEP]
+    need = (2 * n + 31) // 32 * 32                               # keep every slice 128-byte aligned
+    if a[2] != _SINK_STEP or a[1] + need > a[0].numel():
+        return torch.zeros((2, n), dtype=torch.float32, device=device)
+    t = a[0][a[1]:a[1] + 2 * n].view(2, n)
+    a[1] += need
+    return t
+
+
+# nn.BatchNorm2d.num_batches_tracked += 1 is one launch per BatchNorm and forward (62 per step).  With a step protocol
+# (FlatSGD) the increments are collected and applied by one multi-tensor add in FlatSGD.step() / the next zero_grad.
+_DEFER_COUNTERS = False
+_PENDING_COUNTERS = []
+
+
+def defer_counters(on=True):
+    global _DEFER_COUNTERS
+    flush_counters()
+    _DEFER_COUNTERS = bool(on)
+
+
+def count_batch(bn):
+    """Deferred only for a BatchNorm whose weight lives in a FlatSGD's flat buffer: that optimizer's step() flushes."""
+    hit = _GRAD_SINKS.get(id(bn.weight)) if _DEFER_COUNTERS and bn.weight is not None else None
+    if hit is not None and hit[0]() is bn.weight:
+        _PENDING_COUNTERS.append(bn.num_batches_tracked)
+    else:
+        bn.num_batches_tracked += 1
+
+
+def flush_counters():
+    if _PENDING_COUNTERS:
+        with torch.no_grad():
+            torch._foreach_add_(_PENDING_COUNTERS, 1)
+        _PENDING_COUNTERS.clear()
 
 
 def _grad_sink(weight, rows_cols=None):
@@ -254,8 +309,9 @@ def gemm_tn(a1, b, a0=None, k0=0, stats=False, out=None, add=None, add_col0=0):
     d.lda0 = a0.stride(0) if a0 is not None else 0
     colsum = colsq = None
     if stats:
-        sums = torch.zeros((2, n), dtype=torch.float32, device=a1.device)
+        sums = _stat_sums(n, a1.device)
         colsum, colsq = sums[0], sums[1]
+        colsum.sums_buffer = sums                                # the (2, N) tensor itself (its ._base may be a whole arena)
     nbytes = 2 * (m * k + m * n + n * k)
     if add is not None:
         assert not stats and add.shape == (m, n) and add.stride(1) == 1 and add.dtype == torch.bfloat16
@@ -422,7 +478,7 @@ class _Conv1x1(torch.autograd.Function):
         ctx.stats, ctx.passthrough = stats, passthrough
         outs = [_nhwc_from_rows(out, f, h, w)]
         if stats:
-            sums = colsum._base if colsum._base is not None else colsum     # the (2, N) buffer
+            sums = colsum.sums_buffer     # the (2, N) buffer
             ctx.mark_non_differentiable(sums)
             outs.append(sums)
         if passthrough:
@@ -474,7 +530,7 @@ class _MVFConv1x1(torch.autograd.Function):
         ctx.save_for_backward(xk, slab, wb, wt, wh, ww, gamma, beta, running_mean, running_var, save_mean, save_rstd)
         outs = [_nhwc_from_rows(out, f, h, w)]
         if stats:
-            sums = colsum._base if colsum._base is not None else colsum
+            sums = colsum.sums_buffer
             ctx.mark_non_differentiable(sums)
             outs.append(sums)
         if passthrough:
@@ -562,7 +618,7 @@ def conv3x3_raw(x, w_krsc, stride, stats=False):
     d = ConvDesc()
     d.F, d.H, d.W, d.Cin, d.Cout, d.stride, d.ksize = f, h, w, cin, cout, stride, (3 if w_krsc.dim() == 4 else 1)
     out = torch.empty((f, ho, wo, cout), dtype=torch.bfloat16, device=x.device)
-    sums = torch.zeros((2, cout), dtype=torch.float32, device=x.device) if stats else None
+    sums = _stat_sums(cout, x.device) if stats else None
     taps = 9 if w_krsc.dim() == 4 else 1
     mo = f * ho * wo
     with _T("conv3x3" if taps == 9 else "gemm1x1", nbytes=2 * (f * h * w * cin // (1 if taps == 9 else stride * stride)
@@ -761,7 +817,7 @@ class _StemConv(torch.autograd.Function):
         y = _nhwc_from_rows(out, f, ho, wo)
         if not stats:
             return y
-        sums = colsum._base if colsum._base is not None else colsum
+        sums = colsum.sums_buffer
         ctx.mark_non_differentiable(sums)
         return y, sums
 
@@ -908,5 +964,5 @@ def bn_act(x, bn, relu=True, residual=None, sums=None):
         sums = None
     y = _BNAct.apply(x, bn.weight, bn.bias, rm, rv, residual, sums, relu, training, float(bn.eps), momentum)
     if training and bn.track_running_stats:
-        bn.num_batches_tracked += 1
+        count_batch(bn)
     return y

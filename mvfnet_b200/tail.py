@@ -202,6 +202,7 @@ class FlatSGD:
         self._build_transposed_forms()
         (views,) = self.grads.views.values()
         ops.register_grad_sinks(self.params, views)            # weight-gradient kernels write into the flat buffer
+        ops.defer_counters(True)                               # num_batches_tracked: one multi-tensor add per step()
         self.steps = 0
 
     def _build_transposed_forms(self):
@@ -295,6 +296,7 @@ class FlatSGD:
         _lib.check(rc, "sgd_nesterov_step")
         self._transpose()                                                      # W^T / rotated operands of the next backward
         ops.bump_weight_epoch()                                                # derived bf16 forms (W^T, KRSC, ...) are stale
+        ops.flush_counters()                                                   # the step's BatchNorm counters, one launch
         self.steps += 1
 
     # ---- torch.optim.SGD-compatible checkpoint format (utils/checkpoint.py:235-265 stores optimizer.state_dict())

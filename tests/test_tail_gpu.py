@@ -200,9 +200,19 @@ def test_graphed_train_step_matches_eager():
     # 2 x 2 .. 16 x 16 pixels a last-bit difference in a batch statistic moves bf16 roundings downstream.  The graph must
     # stay within that run-to-run spread (measured 2e-3 .. 2e-2 relative here), not within a fixed epsilon.
     e1, e2 = run_eager(), run_eager()
+    # BatchNorm step counters: FlatSGD defers the 62 per-module increments to ONE multi-tensor add in step(); the
+    # state_dict contract (num_batches_tracked == steps taken) must hold after every step, eager and replayed
+    mc, oc = fresh()
+    oc.zero_grad()
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        mc(preprocess_frames(imgs[0]), lbls[0])["loss_cls"].backward()
+    oc.step(1)
+    counters = [v for k, v in mc.state_dict().items() if k.endswith("num_batches_tracked")]
+    assert len(counters) > 50 and all(int(c) == 1 for c in counters)
     m2, o2 = fresh()
     step = GraphedTrainStep(m2, o2, imgs[0], lbls[0], warmup=0)        # capture only: nothing executes, no extra step
     graphed = np.array([step(img, lbl).item() for img, lbl in zip(imgs, lbls)])
+    assert all(int(v) == 4 for k, v in m2.state_dict().items() if k.endswith("num_batches_tracked"))
     spread = np.abs(e1 - e2).max()
     assert np.abs(graphed - e1).max() <= 4 * spread + 5e-3 * np.abs(e1).max(), (e1, e2, graphed)
     assert abs(graphed[0] - e1[0]) <= 4 * abs(e1[0] - e2[0]) + 5e-3 * abs(e1[0]), "the first step sees identical weights"
