@@ -79,6 +79,56 @@ stem_im2col_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restric
 __device__ __forceinline__ float bf_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 
+// The same matrix, one CTA per output row (f, oh): the seven input rows it reads are staged ONCE in shared memory
+// (16-byte global loads, zero padding for the image border written explicitly), then every thread assembles 16-byte
+// chunks from four aligned 32-bit shared-memory loads.  The gather above issues five 4-byte GLOBAL loads per chunk and
+// each warp-level load touches up to eight input rows: L1 throughput 82 %, 1.9 ms for 6.1 GB (profiles/r02_stem_pool_ncu.txt).
+// Element e of an input row lives at byte kRowLead + 2*e of its shared-memory row; a chunk starts at the odd element
+// 6*ow - 9 + 8*j, i.e. at byte 16 + 12*ow + 16*j: always word-aligned.  Needs W % 8 == 0 (16-byte aligned rows).
+constexpr int kRowLead = 34;       // bytes before element 0: 16 + the 9 elements (3 pixels) of left padding
+__global__ void __launch_bounds__(256)
+stem_im2col_rows_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ a, int H, int W, int Ho, int Wo,
+                        int pitch) {
+  extern __shared__ __align__(16) uint8_t srow[];                // 7 rows of `pitch` bytes
+  const int oh = blockIdx.x % Ho;
+  const long long f = blockIdx.x / Ho;
+  const int rowbytes = W * 6;
+  // zero the padding of every row (bytes [0, kRowLead) and [kRowLead + rowbytes, pitch)), and whole rows outside the image
+  const int tailw = (pitch - kRowLead - rowbytes) / 2;
+  for (int i = threadIdx.x; i < 7 * (kRowLead / 2 + tailw); i += 256) {
+    const int r = i / (kRowLead / 2 + tailw), k = i - r * (kRowLead / 2 + tailw);
+    const int off = k < kRowLead / 2 ? 2 * k : kRowLead + rowbytes + 2 * (k - kRowLead / 2);
+    *reinterpret_cast<unsigned short*>(srow + r * pitch + off) = 0;
+  }
+  const int vec = rowbytes / 16;
+  for (int i = threadIdx.x; i < 7 * vec; i += 256) {
+    const int r = i / vec, v = i - r * vec;
+    const int ih = 2 * oh - 3 + r;
+    uint4 q = make_uint4(0u, 0u, 0u, 0u);
+    if (ih >= 0 && ih < H) q = __ldg(reinterpret_cast<const uint4*>(x + (f * H + ih) * (long long)(W * 3)) + v);
+    uint8_t* d = srow + r * pitch + kRowLead + 16 * v;           // 2 (mod 4): halfword, three words, halfword
+    *reinterpret_cast<unsigned short*>(d) = (unsigned short)(q.x & 0xffffu);
+    *reinterpret_cast<uint32_t*>(d + 2) = __funnelshift_r(q.x, q.y, 16);
+    *reinterpret_cast<uint32_t*>(d + 6) = __funnelshift_r(q.y, q.z, 16);
+    *reinterpret_cast<uint32_t*>(d + 10) = __funnelshift_r(q.z, q.w, 16);
+    *reinterpret_cast<unsigned short*>(d + 14) = (unsigned short)(q.w >> 16);
+  }
+  __syncthreads();
+  uint4* out = reinterpret_cast<uint4*>(a) + ((f * Ho + oh) * (long long)Wo) * (kStemKp / 8);
+  const int chunks = Wo * (kStemKp / 8);
+  for (int i = threadIdx.x; i < chunks; i += 256) {
+    const int ow = i / (kStemKp / 8), c = i - ow * (kStemKp / 8);
+    const int kh = c / 3, j = c - kh * 3;
+    uint4 o = make_uint4(0u, 0u, 0u, 0u);
+    if (kh < 7) {
+      const uint32_t* p = reinterpret_cast<const uint32_t*>(srow + kh * pitch + 16 + 12 * ow + 16 * j);
+      o.x = p[0]; o.y = p[1];
+      if (j < 2) { o.z = p[2]; o.w = p[3]; } else { o.z = p[2] & 0xffffu; }   // values 21..23 of a kernel row do not exist
+    }
+    out[i] = o;
+  }
+}
+
 // ---- packed bf16 helpers of the pooling kernels
 __device__ __forceinline__ uint32_t hmax2_nan(uint32_t a, uint32_t b) {        // NaN-propagating maximum of both halves
   uint32_t d;
@@ -347,6 +397,15 @@ int stem_im2col(const void* x, void* a, long long F, int H, int W, mvfb_stream_t
   const int Ho = (H + 6 - 7) / 2 + 1, Wo = (W + 6 - 7) / 2 + 1;
   const long long total = F * Ho * Wo * (kStemKp / 8);
   const unsigned blocks = (unsigned)ceil_div_ll(total, 256);
+  if (W % 8 == 0 && F * Ho < (1LL << 31) && !(reinterpret_cast<uintptr_t>(x) & 15)) {   // one CTA per output row
+    // right padding: the last chunk of a row ends at element 6*(Wo-1) - 9 + 24 <= 3*W + 11
+    const int pitch = ((kRowLead + W * 6 + 24 + 15) / 16) * 16 + 16;
+    stem_im2col_rows_kernel<<<(unsigned)(F * Ho), 256, 7 * pitch, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)x, (__nv_bfloat16*)a, H, W, Ho, Wo, pitch);
+    count_launch();
+    MVFB_LAUNCH_CHECK();
+    return MVFB_OK;
+  }
   if (total < (1LL << 31))
     stem_im2col_kernel<uint32_t><<<blocks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (__nv_bfloat16*)a, H, W, Ho,
                                                                            Wo, total);

@@ -235,13 +235,13 @@ def test_strided_1x1_downsample(F, Cin, Cout, H):
 
 
 # ------------------------------------------------------------------------------------------------ stem
-@pytest.mark.parametrize("F,H", [(2, 224), (3, 64), (1, 30)])
-def test_stem_conv_vs_torch(F, H):
+@pytest.mark.parametrize("F,H,W", [(2, 224, 226), (3, 64, 66), (1, 30, 32), (2, 224, 224), (3, 62, 40), (2, 33, 16)])
+def test_stem_conv_vs_torch(F, H, W):
     """conv1 of the ResNet stem (im2col + tcgen05 GEMM, backbones/resnet.py:424) against torch's fp32 convolution of the
     same bf16-rounded operands: output, the BatchNorm sums of the GEMM epilogue, and the weight gradient."""
     from mvfnet_b200 import ops
     g = torch.Generator().manual_seed(7 + F + H)
-    x = torch.randn((F, 3, H, H + 2), generator=g).cuda()
+    x = torch.randn((F, 3, H, W), generator=g).cuda()          # W % 8 == 0: row-staged im2col kernel, else the gather
     w = (torch.randn((64, 3, 7, 7), generator=g) * 0.1).cuda().requires_grad_(True)
     conv = torch.nn.Conv2d(3, 64, 7, 2, 3, bias=False).cuda()
     with torch.autocast("cuda", dtype=torch.bfloat16):
