@@ -78,7 +78,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   const int split = blockIdx.x / ntile_all, tile = blockIdx.x - split * ntile_all;
   const int nt = tile / a.k_tiles, kt = tile - nt * a.k_tiles;
   // IM2COL: kt enumerates (filter tap rs, channel tile ct); the tap's input pixels are gathered by TMA im2col
-  const int ctiles = a.K / BN;
+  const int ctiles = (a.K + BN - 1) / BN;                      // the last tile may run past K: TMA zero-fills, the epilogue skips
   const int rs = IM2COL ? kt / ctiles : 0, ct = IM2COL ? kt - rs * ctiles : kt;
   const int per = (a.pblocks + a.splits - 1) / a.splits;
   const int pb0 = split * per;
@@ -168,7 +168,8 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       if (row < a.N) {
 #pragma unroll
         for (int q = 0; q < 8; ++q)
-          red_add_v4(dst + c0 + q * 4, __uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
+          if (ct * BN + c0 + q * 4 < a.K)
+            red_add_v4(dst + c0 + q * 4, __uint_as_float(v[q * 4]), __uint_as_float(v[q * 4 + 1]),
                      __uint_as_float(v[q * 4 + 2]), __uint_as_float(v[q * 4 + 3]));
       }
     }
@@ -195,7 +196,7 @@ int launch_wgrad_kernel(const CUtensorMap& tmG, const CUtensorMap& tmX0, const C
                         cudaStream_t st) {
   using C = WCfg<BN>;
   a.n_tiles = (a.N + BM - 1) / BM;
-  a.k_tiles = (a.K / BN) * (IM2COL ? a.ks * a.ks : 1);
+  a.k_tiles = ((a.K + BN - 1) / BN) * (IM2COL ? a.ks * a.ks : 1);
   a.pblocks = (int)((a.M + BKP - 1) / BKP);
   const int tiles = a.n_tiles * a.k_tiles;
   int splits = (2 * num_sms() + tiles - 1) / tiles;            // ~2 CTAs worth of work items per SM
@@ -276,7 +277,9 @@ extern "C" int conv1x1_wgrad(const mvfb_gemm_desc* d, const void* g, const void*
   MVFB_CHECK(!((uintptr_t)g & 15) && !((uintptr_t)x1 & 15) && !((uintptr_t)x0 & 15) && !((uintptr_t)dw & 15),
              MVFB_ERR_UNSUPPORTED, "operands must be 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  if (d->K % 256 == 0) return launch_wgrad<256>(d, g, x0, x1, dw, st);
+  // K = 192 (the stem's patch rows): ONE 256-wide tile with a zero-filled quarter reads dY once; three 64-wide tiles read
+  // it three times and run the N = 64 MMA (2.05 ms for 8.2 GB, profiles/r02_step_by_shape.txt)
+  if (d->K % 256 == 0 || (d->K == 192 && d->K0 == 0)) return launch_wgrad<256>(d, g, x0, x1, dw, st);
   if (d->K % 128 == 0) return launch_wgrad<128>(d, g, x0, x1, dw, st);
   return launch_wgrad<64>(d, g, x0, x1, dw, st);
 }
