@@ -162,7 +162,9 @@ def test_fused_bottleneck_vs_torch_fp32(inpl, planes, hw, stride, mvf, monkeypat
 
 
 @pytest.mark.parametrize("F,Cin,Cout,H,stride", [(2, 64, 64, 56, 1), (4, 128, 128, 28, 1), (8, 256, 256, 14, 1), (16, 512, 512, 7, 1),
-                                                 (2, 128, 128, 56, 2), (4, 256, 256, 28, 2), (4, 512, 512, 14, 2), (3, 64, 192, 9, 1)])
+                                                 (2, 128, 128, 56, 2), (4, 256, 256, 28, 2), (4, 512, 512, 14, 2), (3, 64, 192, 9, 1),
+                                                 # several tiles per CTA (persistent tile loop, both TMEM accumulators in use)
+                                                 (40, 64, 64, 56, 1), (100, 128, 128, 56, 2)])
 def test_conv3x3_implicit_gemm(F, Cin, Cout, H, stride):
     """TMA-im2col implicit GEMM vs torch conv2d in fp32 on the same bf16-rounded operands; forward, fused statistics,
     and the stride-1 input gradient (rotated weights through the same kernel)."""
