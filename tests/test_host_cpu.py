@@ -271,3 +271,35 @@ def test_force_option_and_last_kernel_without_gpu():
     finally:
         _lib.set_option(_lib.OPT_FORCE_FWD, 0)
     assert L.mvf_b200_set_option(99, 1) != 0 and b"unknown option" in L.mvf_b200_last_error()
+
+
+def test_result_io_and_scoring_vs_reference_golden(tmp_path):
+    """mvfnet_b200/results.py (default.pkl dump, top-k / mean-class accuracy, weighted score fusion) against vectors
+    produced by the unmodified reference's codes/core/evaluation/accuracy.py (oracle/make_golden_results.py)."""
+    import numpy as np
+    from conftest import load_cases
+    from mvfnet_b200 import results as R
+    cases = load_cases("results_cases.npz")
+    assert set(cases) == {"small", "k400"}
+    for name, c in cases.items():
+        scores, scores2 = c["scores"].astype(np.float64), c["scores2"].astype(np.float64)
+        labels = [int(v) for v in c["labels"]]
+        assert np.allclose(R.top_k_accuracy(scores, labels, k=(1, 5)), c["top"], atol=1e-12)
+        assert abs(R.mean_class_accuracy(scores, labels) - float(c["mca"])) < 1e-12
+        fused = R.fuse_scores([scores, scores2], [1.0, 0.5])
+        assert np.allclose(R.top_k_accuracy(fused, labels, k=(1, 5)), c["fused_top"], atol=1e-12)
+        if "fused" in c:
+            assert np.allclose(fused, c["fused"], atol=1e-12)
+            assert np.allclose(R.softmax(scores), c["softmax"], atol=1e-12)
+        # default.pkl round trip: per-video (1, classes) outputs -> one (videos, classes) array
+        out = tmp_path / (name + ".pkl")
+        stacked = R.dump_results([row[None, :] for row in scores], str(out))
+        assert stacked.shape == scores.shape and np.array_equal(R.load_results(str(out)), scores)
+        out2 = tmp_path / (name + "_2.pkl")
+        R.dump_results(list(scores2), str(out2))
+        fused2, report = R.fuse_result_files([str(out), str(out2)], [1.0, 0.5], labels=labels)
+        assert np.allclose(fused2, fused) and np.allclose([report["top_k"][1], report["top_k"][5]], c["fused_top"])
+    import pytest
+    with pytest.raises(ValueError):
+        R.dump_results([np.zeros((1, 4))], str(tmp_path / "scores.json"))
+    assert R.top_k_accuracy(np.array([[0.1, 0.9, 0.0]]), [[0, 2]], k=(1, 2)) == [0.0, 1.0]     # multi-label sample
