@@ -172,8 +172,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       }
     }
   } else if (warp == 1) {
-    // ===================== MMA issuer =====================
-    if (lane == 0) {
+    // ===================== MMA issuer (all lanes run the loop, one elected lane issues: ptx.cuh) =====================
+    {
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
       int s = 0;
       uint32_t ph = 0;
@@ -188,17 +188,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           mbar_wait(&full[s], ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(stage_base + (size_t)s * C::kStageBytes);
-          const uint32_t sb = sa + C::kABytes;
+          // one descriptor per operand tile; a K step of 16 elements = 32 bytes = 2 units of the start-address field
+          const uint64_t adesc = umma_smem_desc_sw128(sa, 0, 1024), bdesc = umma_smem_desc_sw128(sa + C::kABytes, 0, 1024);
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) {
-            const uint64_t adesc = umma_smem_desc_sw128(sa + kk * 32, 0, 1024);
-            const uint64_t bdesc = umma_smem_desc_sw128(sb + kk * 32, 0, 1024);
-            umma_f16(d_tmem, adesc, bdesc, idesc, (kb | kk) != 0);
-          }
-          umma_commit(&empty[s]);                              // slot free once these MMAs have read it
+          for (int kk = 0; kk < BK / 16; ++kk) umma_f16_elect(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (kb | kk) != 0);
+          umma_commit_elect(&empty[s]);                        // slot free once these MMAs have read it
           if (++s == C::kStages) { s = 0; ph ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);                          // accumulator complete
+        umma_commit_elect(&tmem_full[acc]);                    // accumulator complete
       }
     }
   } else {
@@ -651,6 +648,8 @@ static int conv3x3_gemm_impl(const mvfb_conv_desc* d, const void* x, const void*
   MVFB_CHECK(!ep.scale || (ep.shift && !((uintptr_t)ep.scale & 15) && !((uintptr_t)ep.shift & 15)), MVFB_ERR_ARG,
              "the epilogue scale needs a shift, both 16-byte aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  // the 56x56 / 28x28 layers: one halo band per tile instead of nine im2col gathers (conv_halo.cu)
+  if (!res && !ep.scale && conv_halo_eligible(d)) return conv_halo(d, x, w, out, colsum, colsq, st);
   if (d->Cout % 256 == 0) return launch_conv3x3<256>(d, x, w, out, colsum, colsq, res, ep, st);
   if (d->Cout % 128 == 0) return launch_conv3x3<128>(d, x, w, out, colsum, colsq, res, ep, st);
   return launch_conv3x3<64>(d, x, w, out, colsum, colsq, res, ep, st);

@@ -135,7 +135,7 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    {                                                          // all lanes run the loop, one elected lane issues (ptx.cuh)
       constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 1, 1);      // both operands MN-major
       int s = 0;
       uint32_t ph = 0;
@@ -143,14 +143,14 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)s * C::kStageBytes);
-        const uint32_t sb = sa + C::kABytes;
+        const uint64_t adesc = desc_mn_sw128(sa), bdesc = desc_mn_sw128(sa + C::kABytes);
 #pragma unroll
-        for (int kk = 0; kk < BKP / 16; ++kk)
-          umma_f16(tmem_base, desc_mn_sw128(sa + kk * 2048), desc_mn_sw128(sb + kk * 2048), idesc, (i | kk) != 0);
-        umma_commit(&empty[s]);
+        for (int kk = 0; kk < BKP / 16; ++kk)                   // 16 pixels = 2 atoms = 2048 bytes = 128 descriptor units
+          umma_f16_elect(tmem_base, adesc + 128u * kk, bdesc + 128u * kk, idesc, (i | kk) != 0);
+        umma_commit_elect(&empty[s]);
         if (++s == C::kStages) { s = 0; ph ^= 1; }
       }
-      umma_commit(done);
+      umma_commit_elect(done);
     }
   } else if (nblocks > 0) {
     // epilogue: TMEM -> registers -> fp32 atomics on dW (rows = output channels of this tile)

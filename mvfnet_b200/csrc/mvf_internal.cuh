@@ -8,6 +8,10 @@ namespace mvfb {
 
 void count_launch(int n = 1);
 
+// conv_halo.cu: 3x3 / stride 1 convolution with the A operand read as shifted views of one halo band
+bool conv_halo_eligible(const mvfb_conv_desc* d);
+int conv_halo(const mvfb_conv_desc* d, const void* x, const void* w, void* out, float* colsum, float* colsq, cudaStream_t st);
+
 // ---- mvf_generic.cu : any layout / dtype / shape
 int mvf_generic_fwd(const mvfb_mvf_desc* d, const void* x, void* y, long long y_stride, const float* wt,
                     const float* wh, const float* ww, const float* gamma, const float* beta, float* rm, float* rv,

@@ -164,7 +164,10 @@ def test_fused_bottleneck_vs_torch_fp32(inpl, planes, hw, stride, mvf, monkeypat
 @pytest.mark.parametrize("F,Cin,Cout,H,stride", [(2, 64, 64, 56, 1), (4, 128, 128, 28, 1), (8, 256, 256, 14, 1), (16, 512, 512, 7, 1),
                                                  (2, 128, 128, 56, 2), (4, 256, 256, 28, 2), (4, 512, 512, 14, 2), (3, 64, 192, 9, 1),
                                                  # several tiles per CTA (persistent tile loop, both TMEM accumulators in use)
-                                                 (40, 64, 64, 56, 1), (100, 128, 128, 56, 2)])
+                                                 (40, 64, 64, 56, 1), (100, 128, 128, 56, 2),
+                                                 # the halo-band kernel (conv_halo.cu): weights resident / streamed, one and
+                                                 # two channel blocks, a frame height whose last tile is mostly padding
+                                                 (60, 128, 128, 28, 1), (50, 64, 128, 28, 1), (40, 128, 64, 56, 1), (90, 64, 64, 30, 1)])
 def test_conv3x3_implicit_gemm(F, Cin, Cout, H, stride):
     """TMA-im2col implicit GEMM vs torch conv2d in fp32 on the same bf16-rounded operands; forward, fused statistics,
     and the stride-1 input gradient (rotated weights through the same kernel)."""
@@ -358,3 +361,22 @@ def test_gemm_bnact_residual_epilogue(M, N, K, relu):
     if relu:
         ref2 = ref2.clamp_min(0)
     assert (nores.float() - ref2).abs().max().item() < 1e-2 * ref2.abs().max().item()
+
+
+def test_conv_halo_matches_im2col_path_bit_for_bit_in_structure():
+    """The halo-band kernel and the im2col kernel compute the same sums in a different order: outputs agree to bf16
+    rounding, the fused statistics to 1e-3, and the option that disables the halo kernel is honoured."""
+    from mvfnet_b200 import ops, _lib
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(48, 64, 56, 56, device="cuda", generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(64, 64, 3, 3, device="cuda", generator=g) / 24).bfloat16().permute(0, 2, 3, 1).contiguous()
+    launches = _lib.launch_count()
+    y1, s1 = ops.conv3x3_raw(x, w, 1, stats=True)
+    assert _lib.launch_count() == launches + 1
+    _lib.set_option(_lib.OPT_CONV_HALO_OFF, 1)
+    try:
+        y2, s2 = ops.conv3x3_raw(x, w, 1, stats=True)
+    finally:
+        _lib.set_option(_lib.OPT_CONV_HALO_OFF, 0)
+    assert rel(y1, y2) < 4e-3 and not torch.isnan(y1.float()).any()
+    assert rel(s1[0], s2[0]) < 2e-3 and rel(s1[1], s2[1]) < 1e-3
