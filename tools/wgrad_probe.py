@@ -24,9 +24,10 @@ for (hw, c, st) in [(56, 64, 1), (28, 128, 1), (14, 256, 1), (7, 512, 1), (56, 1
     ho = (hw - 1) // st + 1
     g = torch.randn(F, c, ho, ho, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
     w = torch.randn(c, c, 3, 3, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
-    d = ops.ConvDesc(); d.F, d.H, d.W, d.Cin, d.Cout, d.stride = F, hw, hw, c, c, st
+    d = ops.ConvDesc(); d.F, d.H, d.W, d.Cin, d.Cout, d.stride, d.ksize = F, hw, hw, c, c, st, 3
     dw = torch.empty(c, 3, 3, c, device="cuda")
     L = ops._L()
+    _lib.check(L.conv3x3_wgrad(C.byref(d), ptr(g), ptr(x), ptr(dw), ops._stream()), 'conv3x3_wgrad')
     a = t(lambda: L.conv3x3_wgrad(C.byref(d), ptr(g), ptr(x), ptr(dw), ops._stream()))
     b = t(lambda: torch.ops.aten.convolution_backward(g, x, w, None, [st, st], [1, 1], [1, 1], False, [0, 0], 1, [False, True, False]))
     print("  hw=%d C=%d s=%d: ours %.0f us, cudnn %.0f us" % (hw, c, st, a, b))
