@@ -112,12 +112,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         tile_geo(tile, nt, f, h0);
         for (int cb = 0; cb < a.cblocks; ++cb) {
           mbar_wait(&band_empty[bs], bph ^ 1);
-#ifdef HALO_NO_LOAD
-          mbar_arrive(&band_full[bs]);
-#else
           mbar_arrive_expect_tx(&band_full[bs], band_tx);
           tma_load_4d(band_base + (size_t)bs * a.band_bytes, &tmX, &band_full[bs], cb * BK, -1, h0 - 1, f);
-#endif
           if (++bs == a.bands) { bs = 0; bph ^= 1; }
           if (!a.bres) {
             for (int tap = 0; tap < 9; ++tap) {
@@ -169,10 +165,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
               tc_fence_after();
               bd = umma_smem_desc_sw128(smem_u32(b_base) + (uint32_t)ss * kBBytes, 0, 1024);
             }
-#ifndef HALO_NO_MMA
 #pragma unroll
             for (int kk = 0; kk < BK / 16; ++kk) umma_f16_elect(d_tmem, ad + 2u * kk, bd + 2u * kk, idesc, (cb | tap | kk) != 0);
-#endif
             if (!a.bres) {
               umma_commit_elect(&b_empty[ss]);
               if (++ss == a.bstages) { ss = 0; sph ^= 1; }
@@ -235,7 +229,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
       named_bar_sync(1, kEpiThreads);
       // store: 16-byte chunks, a warp covers whole rows
-#ifndef HALO_NO_STORE
       {
         constexpr int kChunksPerRow = BN / 8;
 #pragma unroll 4
@@ -249,7 +242,6 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           }
         }
       }
-#endif
       if (a.colsum) {                                          // per-column sums of the rounded tile (gemm_tn.cu's scheme)
         constexpr int kPairs = BN / 2;
         constexpr int kRows = BM / kStatParts;
