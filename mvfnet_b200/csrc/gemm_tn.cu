@@ -357,9 +357,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           for (int rr = 0; rr < kRows; ++rr) {
             const int r = part * kRows + rr;
             const uint32_t h2 = *reinterpret_cast<const uint32_t*>(panel + r * 128 + ((chunk ^ (r & 7)) << 4) + within);
-            const float fa = bf16_lo(h2), fb = bf16_hi(h2);
-            s1a += fa; s1b += fb;
-            s2a = fmaf(fa, fa, s2a); s2b = fmaf(fb, fb, s2b);
+            bf16x2_sum_sq(h2, s1a, s1b, s2a, s2b);
           }
           float* mine = s_stat + (size_t)part * (2 * BN);
           *reinterpret_cast<float2*>(mine + col) = make_float2(s1a, s1b);

@@ -207,6 +207,20 @@ __device__ __forceinline__ uint32_t elect_one() {
       : "=r"(pred));
   return pred;
 }
+// (s1a, s1b) += (lo, hi) of a bf16 pair, (s2a, s2b) += their squares: four mixed-precision FMAs straight from the packed
+// register (products of bf16 values are exact in fp32, x * 1 is x): the same sums as unpack + add + fma in two thirds of the
+// instructions -- the statistics pass of the GEMM epilogues is issue-bound when nothing hides it.
+__device__ __forceinline__ void bf16x2_sum_sq(uint32_t h2, float& s1a, float& s1b, float& s2a, float& s2b) {
+  asm("{\n\t.reg .b16 lo, hi, one;\n\t"
+      "mov.b32 {lo, hi}, %4;\n\t"
+      "mov.b16 one, 0x3f80;\n\t"
+      "fma.rn.f32.bf16 %0, lo, one, %0;\n\t"
+      "fma.rn.f32.bf16 %1, hi, one, %1;\n\t"
+      "fma.rn.f32.bf16 %2, lo, lo, %2;\n\t"
+      "fma.rn.f32.bf16 %3, hi, hi, %3;\n\t}"
+      : "+f"(s1a), "+f"(s1b), "+f"(s2a), "+f"(s2b)
+      : "r"(h2));
+}
 __device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 // bf16 activations imply bf16 stencil taps (the reference's autocast path casts its Conv3d weights): every MVF kernel
