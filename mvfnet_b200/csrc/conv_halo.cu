@@ -344,6 +344,9 @@ int launch_halo(const mvfb_conv_desc* d, const void* x, const void* w, void* out
 // The shapes this kernel is the better choice for (measured, profiles/r02_conv_halo.txt: 394 vs 650 us at C = 64 / 56x56,
 // 295 vs 320 us at C = 128 / 28x28, but 305 vs 233 us at C = 256 / 14x14); everything else stays on the im2col GEMM.
 bool conv_halo_eligible(const mvfb_conv_desc* d) {
+  // a tile is R whole image rows: at least 96 of its 128 MMA rows must be real pixels (W = 64 would give one row = 64)
+  const int rows = (BM + 2) / (d->W + 2);
+  if (rows * d->W < 96) return false;
   return option(OPT_CONV_HALO_OFF) == 0 && d->stride == 1 && d->ksize == 3 && d->W >= 14 && d->W <= 126 && d->Cin % 64 == 0 && d->Cin <= 128 &&
          (d->Cout == 64 || d->Cout % 128 == 0) && (long long)d->F * d->H * (d->W + 2) / BM >= 2 * num_sms();
 }
