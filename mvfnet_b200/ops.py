@@ -700,7 +700,7 @@ class _Conv3x3(torch.autograd.Function):
         elif need_dx and st == 2 and x.shape[2] % 2 == 0 and x.shape[3] % 2 == 0 and s2_dgrad_enabled():
             dx = conv3x3s2_dgrad_raw(g, ctx.weight, x.shape[2], x.shape[3])
             need_dx = False
-        # own 3x3 wgrad where it is within ~1.2x of cuDNN (Cin >= 256: layer3/4); the 9-tap re-read of dY makes it
+        # own 3x3 wgrad for Cin >= 256 (layer3/4: 1.4x cuDNN's time in isolation); the 9-tap re-read of dY makes it
         # 1.5-3.7x slower on the 56x56 / 28x28 layers (tools/wgrad_probe.py), which stay on the library this round
         if need_dw and wgrad_enabled() and (x.shape[1] >= 256 or os.environ.get("MVFB_WGRAD3X3") == "all"):
             sink = _grad_sink(ctx.weight, (wb.shape[0], 9 * x.shape[1]))
@@ -769,7 +769,8 @@ def conv1x1_strided(x, weight, stride, stats=False):
 
 def conv3x3(x, weight, stride=1, stats=False):
     """3x3 / pad 1 bias-free convolution of a bf16 channels_last tensor: forward and stride-1 input-gradient on the
-    tcgen05 implicit GEMM (TMA im2col); weight-gradient and the stride-2 input-gradient are library calls."""
+    tcgen05 implicit GEMM (TMA im2col, or one halo band per tile on the 56x56 / 28x28 layers); stride-2 input gradient =
+    four parity GEMMs (conv3x3s2_dgrad); weight gradient on tcgen05 for Cin >= 256, a library call below that."""
     return _Conv3x3.apply(x, weight, stride, stats)
 
 
