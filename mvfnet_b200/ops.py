@@ -702,8 +702,9 @@ class _Conv3x3(torch.autograd.Function):
             need_dx = False
         # own 3x3 wgrad for Cin >= 256 (layer3/4: 1.4x cuDNN's time in isolation); the 9-tap re-read of dY makes it
         # 1.5-3.7x slower on the 56x56 / 28x28 layers (tools/wgrad_probe.py), which stay on the library this round
-        if need_dw and wgrad_enabled() and (x.shape[1] >= 256 or os.environ.get("MVFB_WGRAD3X3") == "all"):
-            sink = _grad_sink(ctx.weight, (wb.shape[0], 9 * x.shape[1]))
+        own = need_dw and wgrad_enabled() and (x.shape[1] >= 256 or os.environ.get("MVFB_WGRAD3X3") == "all")
+        sink = _grad_sink(ctx.weight, (wb.shape[0], 9 * x.shape[1])) if need_dw else None
+        if own:
             dw = conv3x3_wgrad_raw(g, x, wb.shape[0], st, 3, out=sink)
             dw = sink if sink is not None else dw.permute(0, 3, 1, 2)      # (Cout, Cin, 3, 3) view of KRSC
             need_dw = False
@@ -714,7 +715,11 @@ class _Conv3x3(torch.autograd.Function):
             if need_dx:
                 dx = r[0]
             if need_dw:
-                dw = r[1].float()
+                if sink is not None:
+                    sink.copy_(r[1])
+                    dw = sink
+                else:
+                    dw = r[1].float()
         return dx, dw, None, None
 
 
