@@ -163,7 +163,13 @@ class FlatSGD:
     strides, so channels_last weights stay channels_last), allocates a flat momentum buffer and a flat bf16 copy of the
     parameters (registered with `ops` as the GEMM operands, so the forward launches no cast kernels).  `step()`:
     gradients -> flat buffer (one multi-tensor copy), ONE all-reduce when world > 1, sum of squares, fused update.
-    Nothing in `step()` synchronises with the host.  The state_dict has torch.optim.SGD's format."""
+    Nothing in `step()` synchronises with the host.  The state_dict has torch.optim.SGD's format.
+
+    One deliberate difference from torch.optim.SGD / the reference's `allreduce_grads` (core/dist_utils.py:38-49): a
+    parameter that received NO gradient in a step is treated as having a zero gradient (weight decay and momentum still
+    act on it, on one GPU and on many alike), where torch skips it.  Every parameter of the MVFNet recognizers receives a
+    gradient in every step, so the trajectories coincide (tests/test_tail_gpu.py); a model with unused branches should
+    keep those parameters out of this optimizer."""
 
     def __init__(self, params, lr, momentum=0.0, weight_decay=0.0, nesterov=False, max_norm=None, dampening=0.0):
         from .dist import FlatGrads
