@@ -480,6 +480,7 @@ class _Conv1x1(torch.autograd.Function):
         if stats:
             sums = colsum.sums_buffer     # the (2, N) buffer
             ctx.mark_non_differentiable(sums)
+            ctx.set_materialize_grads(False)   # no zero "gradient" tensor for the statistics output (a fill launch per layer)
             outs.append(sums)
         if passthrough:
             outs.append(x.view_as(x))
@@ -490,6 +491,8 @@ class _Conv1x1(torch.autograd.Function):
         x, wb = ctx.saved_tensors
         f, cin, h, w = x.shape
         g_id = rest[-1] if ctx.passthrough else None
+        if g is None:                                            # the convolution's output was not used: only the identity path
+            return g_id, None, None, None
         g = g.contiguous(memory_format=torch.channels_last)
         g2 = _rows(g)
         dx = dw = None
@@ -532,6 +535,7 @@ class _MVFConv1x1(torch.autograd.Function):
         if stats:
             sums = colsum.sums_buffer
             ctx.mark_non_differentiable(sums)
+            ctx.set_materialize_grads(False)   # no zero "gradient" tensor for the statistics output (a fill launch per layer)
             outs.append(sums)
         if passthrough:
             outs.append(x.view_as(x))
@@ -544,6 +548,8 @@ class _MVFConv1x1(torch.autograd.Function):
         xk, slab, wb, wt, wh, ww, gamma, beta, running_mean, running_var, save_mean, save_rstd = ctx.saved_tensors
         f, c, h, w = xk.shape
         cs = cfg.Cs
+        if g is None:                                            # the block's main path was not used: only the identity path
+            return (rest[-1] if ctx.passthrough else None,) + (None,) * 11
         g = g.contiguous(memory_format=torch.channels_last)
         g2 = _rows(g)
         d = _mvf._make_desc(xk, layout, cfg)
@@ -684,10 +690,13 @@ class _Conv3x3(torch.autograd.Function):
         if not stats:
             return y
         ctx.mark_non_differentiable(sums)
+        ctx.set_materialize_grads(False)   # no zero "gradient" tensor for the statistics output (a fill launch per layer)
         return y, sums
 
     @staticmethod
     def backward(ctx, g, *unused):
+        if g is None:
+            return None, None, None, None
         x, wb = ctx.saved_tensors
         st = ctx.stride
         g = g.contiguous(memory_format=torch.channels_last)
@@ -737,10 +746,13 @@ class _Conv1x1Strided(torch.autograd.Function):
         if not stats:
             return y
         ctx.mark_non_differentiable(sums)
+        ctx.set_materialize_grads(False)   # no zero "gradient" tensor for the statistics output (a fill launch per layer)
         return y, sums
 
     @staticmethod
     def backward(ctx, g, *unused):
+        if g is None:
+            return None, None, None, None
         x, wb = ctx.saved_tensors
         st = ctx.stride
         f, cin, h, w = x.shape
@@ -825,13 +837,14 @@ class _StemConv(torch.autograd.Function):
             return y
         sums = colsum.sums_buffer
         ctx.mark_non_differentiable(sums)
+        ctx.set_materialize_grads(False)   # no zero "gradient" tensor for the statistics output (a fill launch per layer)
         return y, sums
 
     @staticmethod
     def backward(ctx, g, *unused):
         (a,) = ctx.saved_tensors
         dw = None
-        if ctx.needs_input_grad[1]:
+        if g is not None and ctx.needs_input_grad[1]:
             g2 = _rows(g.contiguous(memory_format=torch.channels_last))
             dw = gemm_wgrad(g2, a).view(64, 8, 24)[:, :7, :21].reshape(64, 7, 7, 3).permute(0, 3, 1, 2).to(ctx.wdtype)
         return None, dw, None
