@@ -86,7 +86,9 @@ def _L():
 
 
 def _stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # the raw handle of the current stream of the current device: two C calls (torch.cuda.current_stream() builds a Stream
+    # object through several Python layers, ~16 us -- 270 launches per step made that a quarter of the host time at B = 12)
+    return C.c_void_p(torch._C._cuda_getCurrentRawStream(torch._C._cuda_getDevice()))
 
 
 _T = _mvf._Timed          # bench.py's per-family launch timing (no-op unless mvf.timing_begin() was called)
