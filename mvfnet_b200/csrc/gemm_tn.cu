@@ -221,9 +221,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
-      // staging tile of the previous store must have been read by the TMA engine
-      if (et == 0) tma_store_wait_read<0>();
+      const uint8_t* add_tile = RES ? addend + (size_t)acc * C::kStagingBytes : staging;
+      // Two phases where the tile has at least two 64-column panels and no statistics are wanted: convert the first half
+      // of the columns, hand its panels to the TMA engine, convert the second half while they are being read.  With one
+      // phase the store of tile i and the conversion of tile i+1 take turns on the single staging buffer (163 -> 148 us,
+      // 243 -> 228 us on the wide-N / small-K input-gradient GEMMs); WITH statistics the one-phase order is the faster one,
+      // because there the statistics pass is what overlaps the store (profiles/r02_conv_halo.txt, GEMM ablations).
+      const bool two_phase = C::kPanels >= 2 && !a.scat && !a.colsum && !(a.res && !RES);
+      const int nphase = two_phase ? 2 : 1;
+      for (int phase = 0; phase < nphase; ++phase) {
+      // the panels this phase writes must have been read by the TMA engine (two-phase: one younger store group may still
+      // be pending -- the other half's)
+      if (et == 0) { if (two_phase) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
       named_bar_sync(1, kEpiThreads);
+      if (phase == 0) {
       // optional addend (out = A B^T + res): its 128 x BN tile is copied into the staging buffer FIRST, coalesced (a
       // warp reads whole 128- .. 512-byte rows), in the swizzled layout the results will have -- while this tile's MMAs
       // are still running.  Each thread later adds its own row chunks from shared memory (the first version read the
@@ -243,11 +254,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       tc_fence_after();
       if (!RES && a.res) named_bar_sync(1, kEpiThreads);       // every addend chunk is in place
       if (RES) mbar_wait(&res_full[acc], acc_ph);              // this tile's addend has landed (requested two tiles ago)
-      const uint8_t* add_tile = RES ? addend + (size_t)acc * C::kStagingBytes : staging;
-      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN + half * kHalfN) + ((uint32_t)(lane_grp * 32) << 16);
+      }
+      // columns of this warp in this phase: one phase = its half of the tile; two phases = a quarter each
+      const int colbase = two_phase ? phase * kHalfN + half * (kHalfN / 2) : half * kHalfN;
+      const int ncols = two_phase ? kHalfN / 2 : kHalfN;
+      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN + colbase) + ((uint32_t)(lane_grp * 32) << 16);
 #pragma unroll 1
-      for (int cc = 0; cc < kHalfN; cc += 32) {
-        const int c0 = half * kHalfN + cc;                     // first column of this chunk within the tile
+      for (int cc = 0; cc < ncols; cc += 32) {
+        const int c0 = colbase + cc;                           // first column of this chunk within the tile
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + cc, v);
         tmem_ld_wait();
@@ -293,6 +307,27 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           *reinterpret_cast<uint4*>(panel + (((chunk0 + q) ^ (row & 7)) << 4)) = o;
         }
       }
+      if (two_phase) {
+        if (phase == 1) {                                      // TMEM accumulator fully read: hand it back to the MMA warp
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        fence_proxy_async_smem();                              // staging writes -> visible to the TMA engine
+        named_bar_sync(1, kEpiThreads);
+        if (et == 0) {
+#pragma unroll
+          for (int p = 0; p < C::kPanels / 2; ++p) {
+            const int pp = phase * (C::kPanels / 2) + p;
+            tma_store_2d(&tmD, staging + (size_t)pp * (BM * 128), nt * BN + pp * 64, mt * BM);
+          }
+          tma_store_commit();
+          // every epilogue thread has read this tile's addend (the barrier above): its buffer takes the tile after next
+          if (RES && phase == 1 && tile + 2 * (int)gridDim.x < total_tiles) request_addend(tile + 2 * (int)gridDim.x, acc);
+        }
+      }
+      }                                                        // phases
+      if (!two_phase) {
       if (a.scat && et < BM) {                                 // destination of tile row `et` (M < 2^31: checked by the host)
         const unsigned m = (unsigned)mt * BM + et;
         long long off = -1;
@@ -340,6 +375,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // every epilogue thread has read this tile's addend (the barrier above): its buffer takes the tile after next
         if (RES && tile + 2 * (int)gridDim.x < total_tiles) request_addend(tile + 2 * (int)gridDim.x, acc);
       }
+      }                                                        // !two_phase
       // per-column statistics of the rounded tile (rows beyond M were zero-filled by TMA: they add nothing).  A work
       // item is (column pair, row part): one 32-bit shared-memory load yields two columns of a row, consecutive threads
       // take consecutive column pairs (conflict-free whatever the swizzle: the 32 words of a warp lie in one 128-byte row)
