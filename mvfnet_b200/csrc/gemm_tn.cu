@@ -230,151 +230,151 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       const bool two_phase = C::kPanels >= 2 && !a.scat && !a.colsum && !(a.res && !RES);
       const int nphase = two_phase ? 2 : 1;
       for (int phase = 0; phase < nphase; ++phase) {
-      // the panels this phase writes must have been read by the TMA engine (two-phase: one younger store group may still
-      // be pending -- the other half's)
-      if (et == 0) { if (two_phase) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
-      named_bar_sync(1, kEpiThreads);
-      if (phase == 0) {
-      // optional addend (out = A B^T + res): its 128 x BN tile is copied into the staging buffer FIRST, coalesced (a
-      // warp reads whole 128- .. 512-byte rows), in the swizzled layout the results will have -- while this tile's MMAs
-      // are still running.  Each thread later adds its own row chunks from shared memory (the first version read the
-      // addend row-wise from global memory per thread: 32 cache lines per load instruction, 3.5 ms per step).
-      if (!RES && a.res) {
-        constexpr int kChunksPerRow = BN / 8;                    // 16-byte chunks per tile row
-        const long long m0 = (long long)mt * BM;
+        // the panels this phase writes must have been read by the TMA engine (two-phase: one younger store group may still
+        // be pending -- the other half's)
+        if (et == 0) { if (two_phase) tma_store_wait_read<1>(); else tma_store_wait_read<0>(); }
+        named_bar_sync(1, kEpiThreads);
+        if (phase == 0) {
+          // optional addend (out = A B^T + res): its 128 x BN tile is copied into the staging buffer FIRST, coalesced (a
+          // warp reads whole 128- .. 512-byte rows), in the swizzled layout the results will have -- while this tile's MMAs
+          // are still running.  Each thread later adds its own row chunks from shared memory (the first version read the
+          // addend row-wise from global memory per thread: 32 cache lines per load instruction, 3.5 ms per step).
+          if (!RES && a.res) {
+            constexpr int kChunksPerRow = BN / 8;                    // 16-byte chunks per tile row
+            const long long m0 = (long long)mt * BM;
 #pragma unroll 4
-        for (int idx = et; idx < BM * kChunksPerRow; idx += kEpiThreads) {
-          const int r = idx / kChunksPerRow, ch = idx - r * kChunksPerRow;
-          uint4 v4 = make_uint4(0u, 0u, 0u, 0u);
-          if (m0 + r < a.M) v4 = __ldg(reinterpret_cast<const uint4*>(a.res + (m0 + r) * a.ldr + nt * BN + ch * 8));
-          *reinterpret_cast<uint4*>(staging + (size_t)(ch >> 3) * (BM * 128) + (size_t)r * 128 + (((ch & 7) ^ (r & 7)) << 4)) = v4;
-        }
-      }
-      mbar_wait(&tmem_full[acc], acc_ph);
-      tc_fence_after();
-      if (!RES && a.res) named_bar_sync(1, kEpiThreads);       // every addend chunk is in place
-      if (RES) mbar_wait(&res_full[acc], acc_ph);              // this tile's addend has landed (requested two tiles ago)
-      }
-      // columns of this warp in this phase: one phase = its half of the tile; two phases = a quarter each
-      const int colbase = two_phase ? phase * kHalfN + half * (kHalfN / 2) : half * kHalfN;
-      const int ncols = two_phase ? kHalfN / 2 : kHalfN;
-      const uint32_t taddr = tmem_base + (uint32_t)(acc * BN + colbase) + ((uint32_t)(lane_grp * 32) << 16);
-#pragma unroll 1
-      for (int cc = 0; cc < ncols; cc += 32) {
-        const int c0 = colbase + cc;                           // first column of this chunk within the tile
-        uint32_t v[32];
-        tmem_ld_32x32b_x32(taddr + cc, v);
-        tmem_ld_wait();
-        if (a.ep_scale) {                                      // every lane reads the same 32 floats: L1 broadcast
-          const float4* sc = reinterpret_cast<const float4*>(a.ep_scale + nt * BN + c0);
-          const float4* sh = reinterpret_cast<const float4*>(a.ep_shift + nt * BN + c0);
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float4 s4 = __ldg(sc + q), h4 = __ldg(sh + q);
-            v[4 * q + 0] = __float_as_uint(fmaf(__uint_as_float(v[4 * q + 0]), s4.x, h4.x));
-            v[4 * q + 1] = __float_as_uint(fmaf(__uint_as_float(v[4 * q + 1]), s4.y, h4.y));
-            v[4 * q + 2] = __float_as_uint(fmaf(__uint_as_float(v[4 * q + 2]), s4.z, h4.z));
-            v[4 * q + 3] = __float_as_uint(fmaf(__uint_as_float(v[4 * q + 3]), s4.w, h4.w));
+            for (int idx = et; idx < BM * kChunksPerRow; idx += kEpiThreads) {
+              const int r = idx / kChunksPerRow, ch = idx - r * kChunksPerRow;
+              uint4 v4 = make_uint4(0u, 0u, 0u, 0u);
+              if (m0 + r < a.M) v4 = __ldg(reinterpret_cast<const uint4*>(a.res + (m0 + r) * a.ldr + nt * BN + ch * 8));
+              *reinterpret_cast<uint4*>(staging + (size_t)(ch >> 3) * (BM * 128) + (size_t)r * 128 + (((ch & 7) ^ (r & 7)) << 4)) = v4;
+            }
           }
+          mbar_wait(&tmem_full[acc], acc_ph);
+          tc_fence_after();
+          if (!RES && a.res) named_bar_sync(1, kEpiThreads);       // every addend chunk is in place
+          if (RES) mbar_wait(&res_full[acc], acc_ph);              // this tile's addend has landed (requested two tiles ago)
         }
-        uint8_t* panel = staging + (size_t)(c0 >> 6) * (BM * 128) + (size_t)row * 128;
-        const uint8_t* apanel = add_tile + (size_t)(c0 >> 6) * (BM * 128) + (size_t)row * 128;
-        const int chunk0 = (c0 & 63) >> 3;
-        if (a.res && nt * BN + c0 >= a.res_col0) {             // this thread's own row chunks of the staged addend
+        // columns of this warp in this phase: one phase = its half of the tile; two phases = a quarter each
+        const int colbase = two_phase ? phase * kHalfN + half * (kHalfN / 2) : half * kHalfN;
+        const int ncols = two_phase ? kHalfN / 2 : kHalfN;
+        const uint32_t taddr = tmem_base + (uint32_t)(acc * BN + colbase) + ((uint32_t)(lane_grp * 32) << 16);
+#pragma unroll 1
+        for (int cc = 0; cc < ncols; cc += 32) {
+          const int c0 = colbase + cc;                           // first column of this chunk within the tile
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + cc, v);
+          tmem_ld_wait();
+          if (a.ep_scale) {                                      // every lane reads the same 32 floats: L1 broadcast
+            const float4* sc = reinterpret_cast<const float4*>(a.ep_scale + nt * BN + c0);
+            const float4* sh = reinterpret_cast<const float4*>(a.ep_shift + nt * BN + c0);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 s4 = __ldg(sc + q), h4 = __ldg(sh + q);
+              v[4 * q + 0] = __float_as_uint(fmaf(__uint_as_float(v[4 * q + 0]), s4.x, h4.x));
+              v[4 * q + 1] = __float_as_uint(fmaf(__uint_as_float(v[4 * q + 1]), s4.y, h4.y));
+              v[4 * q + 2] = __float_as_uint(fmaf(__uint_as_float(v[4 * q + 2]), s4.z, h4.z));
+              v[4 * q + 3] = __float_as_uint(fmaf(__uint_as_float(v[4 * q + 3]), s4.w, h4.w));
+            }
+          }
+          uint8_t* panel = staging + (size_t)(c0 >> 6) * (BM * 128) + (size_t)row * 128;
+          const uint8_t* apanel = add_tile + (size_t)(c0 >> 6) * (BM * 128) + (size_t)row * 128;
+          const int chunk0 = (c0 & 63) >> 3;
+          if (a.res && nt * BN + c0 >= a.res_col0) {             // this thread's own row chunks of the staged addend
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const uint4 r4 = *reinterpret_cast<const uint4*>(apanel + (((chunk0 + q) ^ (row & 7)) << 4));
+              const uint32_t w4[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                v[q * 8 + 2 * e] = __float_as_uint(__uint_as_float(v[q * 8 + 2 * e]) + bf16_lo(w4[e]));
+                v[q * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(v[q * 8 + 2 * e + 1]) + bf16_hi(w4[e]));
+              }
+            }
+          }
+          if (a.ep_relu) {
+#pragma unroll
+            for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(fmaxf(__uint_as_float(v[q]), 0.f));
+          }
+          // 32 fp32 -> 32 bf16 = 64 B = four 16-byte chunks of this row in panel c0/64
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
-            const uint4 r4 = *reinterpret_cast<const uint4*>(apanel + (((chunk0 + q) ^ (row & 7)) << 4));
-            const uint32_t w4[4] = {r4.x, r4.y, r4.z, r4.w};
+            uint4 o;
+            o.x = pack_bf16(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
+            o.y = pack_bf16(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
+            o.z = pack_bf16(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
+            o.w = pack_bf16(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
+            *reinterpret_cast<uint4*>(panel + (((chunk0 + q) ^ (row & 7)) << 4)) = o;
+          }
+        }
+        if (two_phase) {
+          if (phase == 1) {                                      // TMEM accumulator fully read: hand it back to the MMA warp
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          }
+          fence_proxy_async_smem();                              // staging writes -> visible to the TMA engine
+          named_bar_sync(1, kEpiThreads);
+          if (et == 0) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              v[q * 8 + 2 * e] = __float_as_uint(__uint_as_float(v[q * 8 + 2 * e]) + bf16_lo(w4[e]));
-              v[q * 8 + 2 * e + 1] = __float_as_uint(__uint_as_float(v[q * 8 + 2 * e + 1]) + bf16_hi(w4[e]));
+            for (int p = 0; p < C::kPanels / 2; ++p) {
+              const int pp = phase * (C::kPanels / 2) + p;
+              tma_store_2d(&tmD, staging + (size_t)pp * (BM * 128), nt * BN + pp * 64, mt * BM);
             }
+            tma_store_commit();
+            // every epilogue thread has read this tile's addend (the barrier above): its buffer takes the tile after next
+            if (RES && phase == 1 && tile + 2 * (int)gridDim.x < total_tiles) request_addend(tile + 2 * (int)gridDim.x, acc);
           }
         }
-        if (a.ep_relu) {
-#pragma unroll
-          for (int q = 0; q < 32; ++q) v[q] = __float_as_uint(fmaxf(__uint_as_float(v[q]), 0.f));
-        }
-        // 32 fp32 -> 32 bf16 = 64 B = four 16-byte chunks of this row in panel c0/64
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint4 o;
-          o.x = pack_bf16(__uint_as_float(v[q * 8 + 0]), __uint_as_float(v[q * 8 + 1]));
-          o.y = pack_bf16(__uint_as_float(v[q * 8 + 2]), __uint_as_float(v[q * 8 + 3]));
-          o.z = pack_bf16(__uint_as_float(v[q * 8 + 4]), __uint_as_float(v[q * 8 + 5]));
-          o.w = pack_bf16(__uint_as_float(v[q * 8 + 6]), __uint_as_float(v[q * 8 + 7]));
-          *reinterpret_cast<uint4*>(panel + (((chunk0 + q) ^ (row & 7)) << 4)) = o;
-        }
-      }
-      if (two_phase) {
-        if (phase == 1) {                                      // TMEM accumulator fully read: hand it back to the MMA warp
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-        }
-        fence_proxy_async_smem();                              // staging writes -> visible to the TMA engine
-        named_bar_sync(1, kEpiThreads);
-        if (et == 0) {
-#pragma unroll
-          for (int p = 0; p < C::kPanels / 2; ++p) {
-            const int pp = phase * (C::kPanels / 2) + p;
-            tma_store_2d(&tmD, staging + (size_t)pp * (BM * 128), nt * BN + pp * 64, mt * BM);
-          }
-          tma_store_commit();
-          // every epilogue thread has read this tile's addend (the barrier above): its buffer takes the tile after next
-          if (RES && phase == 1 && tile + 2 * (int)gridDim.x < total_tiles) request_addend(tile + 2 * (int)gridDim.x, acc);
-        }
-      }
       }                                                        // phases
       if (!two_phase) {
-      if (a.scat && et < BM) {                                 // destination of tile row `et` (M < 2^31: checked by the host)
-        const unsigned m = (unsigned)mt * BM + et;
-        long long off = -1;
-        if (m < (unsigned)a.M) {
-          const unsigned j = m % (unsigned)a.Wo, pq = m / (unsigned)a.Wo;
-          const unsigned i = pq % (unsigned)a.Ho, f = pq / (unsigned)a.Ho;
-          off = (((long long)f * (2 * a.Ho) + 2 * i) * (2 * a.Wo) + 2 * j) * (long long)a.N;
+        if (a.scat && et < BM) {                                 // destination of tile row `et` (M < 2^31: checked by the host)
+          const unsigned m = (unsigned)mt * BM + et;
+          long long off = -1;
+          if (m < (unsigned)a.M) {
+            const unsigned j = m % (unsigned)a.Wo, pq = m / (unsigned)a.Wo;
+            const unsigned i = pq % (unsigned)a.Ho, f = pq / (unsigned)a.Ho;
+            off = (((long long)f * (2 * a.Ho) + 2 * i) * (2 * a.Wo) + 2 * j) * (long long)a.N;
+          }
+          reinterpret_cast<long long*>(s_stat)[et] = off;
         }
-        reinterpret_cast<long long*>(s_stat)[et] = off;
-      }
-      // TMEM accumulator fully read: hand it back to the MMA warp
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      fence_proxy_async_smem();                                // staging writes -> visible to the TMA engine
-      named_bar_sync(1, kEpiThreads);
-      if (a.scat) {
-        // every output row is a pixel of its own in the double-resolution image: 16-byte chunks, a warp covers whole rows
-        // (row offsets were computed once per tile, before the barrier above: s_rowoff).  scat_fill: the row owns its
-        // whole 2 x 2 cell and zeroes the other three pixels (stride-2 1x1 input gradient: dx needs no memset).
-        constexpr int kChunksPerRow = BN / 8;
-        const long long* s_rowoff = reinterpret_cast<const long long*>(s_stat);
-        const long long right = a.N, down = 2ll * a.Wo * a.N;      // one pixel to the right / one image row down, in elements
+        // TMEM accumulator fully read: hand it back to the MMA warp
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        fence_proxy_async_smem();                                // staging writes -> visible to the TMA engine
+        named_bar_sync(1, kEpiThreads);
+        if (a.scat) {
+          // every output row is a pixel of its own in the double-resolution image: 16-byte chunks, a warp covers whole rows
+          // (row offsets were computed once per tile, before the barrier above: s_rowoff).  scat_fill: the row owns its
+          // whole 2 x 2 cell and zeroes the other three pixels (stride-2 1x1 input gradient: dx needs no memset).
+          constexpr int kChunksPerRow = BN / 8;
+          const long long* s_rowoff = reinterpret_cast<const long long*>(s_stat);
+          const long long right = a.N, down = 2ll * a.Wo * a.N;      // one pixel to the right / one image row down, in elements
 #pragma unroll 4
-        for (int idx = et; idx < BM * kChunksPerRow; idx += kEpiThreads) {
-          const int r = idx / kChunksPerRow, ch = idx - r * kChunksPerRow;
-          const long long off = s_rowoff[r];
-          if (off >= 0) {
-            const uint4 v4 = *reinterpret_cast<const uint4*>(staging + (size_t)(ch >> 3) * (BM * 128) + (size_t)r * 128 +
-                                                             (((ch & 7) ^ (r & 7)) << 4));
-            __nv_bfloat16* dst = a.scat + off + nt * BN + ch * 8;
-            *reinterpret_cast<uint4*>(dst) = v4;
-            if (a.scat_fill) {
-              const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
-              *reinterpret_cast<uint4*>(dst + right) = z4;
-              *reinterpret_cast<uint4*>(dst + down) = z4;
-              *reinterpret_cast<uint4*>(dst + down + right) = z4;
+          for (int idx = et; idx < BM * kChunksPerRow; idx += kEpiThreads) {
+            const int r = idx / kChunksPerRow, ch = idx - r * kChunksPerRow;
+            const long long off = s_rowoff[r];
+            if (off >= 0) {
+              const uint4 v4 = *reinterpret_cast<const uint4*>(staging + (size_t)(ch >> 3) * (BM * 128) + (size_t)r * 128 +
+                                                               (((ch & 7) ^ (r & 7)) << 4));
+              __nv_bfloat16* dst = a.scat + off + nt * BN + ch * 8;
+              *reinterpret_cast<uint4*>(dst) = v4;
+              if (a.scat_fill) {
+                const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+                *reinterpret_cast<uint4*>(dst + right) = z4;
+                *reinterpret_cast<uint4*>(dst + down) = z4;
+                *reinterpret_cast<uint4*>(dst + down + right) = z4;
+              }
             }
           }
-        }
-      } else if (et == 0) {
+        } else if (et == 0) {
 #pragma unroll
-        for (int p = 0; p < C::kPanels; ++p) tma_store_2d(&tmD, staging + (size_t)p * (BM * 128), nt * BN + p * 64, mt * BM);
-        tma_store_commit();
-        // every epilogue thread has read this tile's addend (the barrier above): its buffer takes the tile after next
-        if (RES && tile + 2 * (int)gridDim.x < total_tiles) request_addend(tile + 2 * (int)gridDim.x, acc);
-      }
+          for (int p = 0; p < C::kPanels; ++p) tma_store_2d(&tmD, staging + (size_t)p * (BM * 128), nt * BN + p * 64, mt * BM);
+          tma_store_commit();
+          // every epilogue thread has read this tile's addend (the barrier above): its buffer takes the tile after next
+          if (RES && tile + 2 * (int)gridDim.x < total_tiles) request_addend(tile + 2 * (int)gridDim.x, acc);
+        }
       }                                                        // !two_phase
       // per-column statistics of the rounded tile (rows beyond M were zero-filled by TMA: they add nothing).  A work
       // item is (column pair, row part): one 32-bit shared-memory load yields two columns of a row, consecutive threads
