@@ -51,9 +51,10 @@ const char* mvf_b200_last_kernel(void);
  *   MVFB_OPT_FORCE_FWD / MVFB_OPT_FORCE_BWD: 0 = automatic tier selection (default), else one of MVFB_KERNEL_*: only
  *       that tier may serve mvf_fwd / mvf_bwd -- a descriptor it cannot serve fails with MVFB_ERR_UNSUPPORTED;
  *   MVFB_OPT_CONV_HALO_OFF: 1 = conv3x3_gemm never takes the halo-band kernel (A/B measurements, tests of the im2col path).
+ *   MVFB_OPT_GEMM_PAIR_OFF: 1 = the GEMM kernels never launch as CTA pairs (tcgen05 cta_group::2).
  *   MVFB_OPT_SWEEP_DEBUG: 1 = the sweep forward kernel writes %globaltimer stamps at workspace + 512 KiB (needs a
  *       workspace of >= 1 MiB; tools/stream_timeline.py). */
-enum { MVFB_OPT_FORCE_FWD = 0, MVFB_OPT_FORCE_BWD = 1, MVFB_OPT_SWEEP_DEBUG = 2, MVFB_OPT_CONV_HALO_OFF = 3 };
+enum { MVFB_OPT_FORCE_FWD = 0, MVFB_OPT_FORCE_BWD = 1, MVFB_OPT_SWEEP_DEBUG = 2, MVFB_OPT_CONV_HALO_OFF = 3, MVFB_OPT_GEMM_PAIR_OFF = 4 };
 enum { MVFB_KERNEL_AUTO = 0, MVFB_KERNEL_SWEEP = 1, MVFB_KERNEL_STREAM = 2, MVFB_KERNEL_RING = 3, MVFB_KERNEL_GENERIC = 4 };
 int mvf_b200_set_option(int key, int value);
 

@@ -15,7 +15,7 @@ MVFB_F32, MVFB_BF16 = 0, 1
 MVFB_NCHW, MVFB_NHWC = 0, 1
 MODES = {"T": 0, "TH": 1, "THW": 2}
 # mvf_b200_set_option keys / kernel tiers (include/mvf_b200.h)
-OPT_FORCE_FWD, OPT_FORCE_BWD, OPT_SWEEP_DEBUG, OPT_CONV_HALO_OFF = 0, 1, 2, 3
+OPT_FORCE_FWD, OPT_FORCE_BWD, OPT_SWEEP_DEBUG, OPT_CONV_HALO_OFF, OPT_GEMM_PAIR_OFF = 0, 1, 2, 3, 4
 KERNELS = {"auto": 0, "sweep": 1, "stream": 2, "ring": 3, "generic": 4}
 
 

@@ -56,7 +56,7 @@ struct DevOnce {
 // Kernel family that served the last mvf_fwd / mvf_bwd call of this thread (mvf_b200_last_kernel()).
 void note_kernel(const char* name);
 // Test / tool knobs set through mvf_b200_set_option() (never read from the environment).
-enum { OPT_FORCE_FWD = 0, OPT_FORCE_BWD = 1, OPT_SWEEP_DEBUG = 2, OPT_CONV_HALO_OFF = 3, OPT_COUNT };
+enum { OPT_FORCE_FWD = 0, OPT_FORCE_BWD = 1, OPT_SWEEP_DEBUG = 2, OPT_CONV_HALO_OFF = 3, OPT_GEMM_PAIR_OFF = 4, OPT_COUNT };
 int option(int key);
 
 // Encode a tiled TMA descriptor. dims/strides innermost first; strides in BYTES for dims 1..rank-1

@@ -60,12 +60,13 @@ struct GemmArgs {
   int scat_fill;                   // 1: also zero the three other pixels of the row's 2 x 2 cell
 };
 
-template <int BN, bool RES = false>
+template <int BN, bool RES = false, int CL = 1>
 struct Cfg {
-  // RES (addend tile prefetched by TMA into two buffers of its own): fewer stages make room for them
-  static constexpr int kStages = RES ? (BN >= 128 ? 3 : 4) : (BN >= 256 ? 3 : (BN >= 128 ? 5 : 6));
+  // RES (addend tile prefetched by TMA into two buffers of its own): fewer stages make room for them.  CL = 2 (CTA pair):
+  // a CTA holds half of every B tile, which buys a fourth stage at BN = 256
+  static constexpr int kStages = RES ? (BN >= 128 ? 3 : 4) : (BN >= 256 ? (CL == 2 ? 4 : 3) : (BN >= 128 ? 5 : 6));
   static constexpr int kABytes = BM * BK * 2;                 // 16 KB
-  static constexpr int kBBytes = BN * BK * 2;
+  static constexpr int kBBytes = BN * BK * 2 / CL;            // this CTA's share of the B tile
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kPanels = BN / 64;                     // 64-column (128 B) panels of the output tile
   static constexpr int kStagingBytes = BM * BN * 2;
@@ -86,12 +87,19 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 // with __ldg inside the epilogue: on the K <= 128 layers, where the epilogue IS the critical path, the fused add cost
 // as much as the separate add kernel it replaced -- profiles/r02_step_by_shape.txt.)  RES = false with a.res set is
 // that older in-epilogue copy, kept for the im2col kernels (inference only).
-template <int BN, bool IM2COL, bool RES>
+// CL = 2: CTA pairs (clusters of two, tcgen05 cta_group::2).  The pair computes a 256-row tile of ONE N tile: each CTA loads
+// its own 128 rows of A and HALF of the B tile, the leader (cluster rank 0) issues M = 256 MMAs over both CTAs' shared
+// memory, each CTA's epilogue drains its own 128 accumulator rows.  A CTA then pulls A + B/2 instead of A + B through its
+// L2 -> SM port, which is what paces the K >= 256 layers (profiles/r02_conv_halo.txt, GEMM ablations).  Barriers: all TMA
+// loads of both CTAs complete on the LEADER's full[s]; the leader's MMA commits arrive on empty[s] / tmem_full[acc] of
+// BOTH CTAs; both CTAs' epilogue warps arrive on the LEADER's tmem_empty[acc].
+template <int BN, bool IM2COL, bool RES, int CL = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmA1,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
                const __grid_constant__ CUtensorMap tmR, const GemmArgs a) {
-  using C = Cfg<BN, RES>;
+  using C = Cfg<BN, RES, CL>;
+  static_assert(CL == 1 || (CL == 2 && !RES), "the CTA-pair mode has no addend path");
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stage_base = smem;                                        // kStages x [A tile | B tile]
@@ -110,6 +118,12 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kblocks = a.K / BK;
   const int total_tiles = a.m_tiles * a.n_tiles;
+  // tile loop of this CTA: plain = tiles blockIdx.x, +gridDim.x, ...; pair = PAIR tiles (two M tiles, one N tile), the
+  // CTA's own M tile being 2 * pair + rank
+  const int crank = CL == 2 ? (int)cluster_ctarank() : 0;
+  const int t_first = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_step = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int t_limit = CL == 2 ? ((a.m_tiles + 1) / 2) * a.n_tiles : total_tiles;
 
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&tmA0);
@@ -122,18 +136,23 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tmem_full[s], 1);
-      mbar_init(&tmem_empty[s], kEpiThreads / 32);
+      mbar_init(&tmem_empty[s], (kEpiThreads / 32) * CL);     // pair: the leader's barrier counts both CTAs' epilogue warps
       mbar_init(&res_full[s], 1);
     }
     if (RES) tma_prefetch_desc(&tmR);
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, C::kTmemCols);
-    tmem_relinquish();
+    if (CL == 2) {
+      tmem_alloc_pair(tmem_slot, C::kTmemCols);
+    } else {
+      tmem_alloc(tmem_slot, C::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();             // the peer's barriers exist before anything is sent to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -142,8 +161,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+      for (int tile = t_first; tile < t_limit; tile += t_step) {
+        const int mt = (CL == 2 ? 2 : 1) * (tile / a.n_tiles) + crank, nt = tile % a.n_tiles;
         // IM2COL: first output pixel of the tile -> base input pixel of its filter window (pad 1)
         int bw = 0, bh = 0, bn = 0, cblocks = 1;
         if (IM2COL) {
@@ -158,30 +177,43 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* sa = stage_base + (size_t)s * C::kStageBytes;
-          mbar_arrive_expect_tx(&full[s], C::kStageBytes);
           const int k = kb * BK;
-          if (IM2COL) {
-            tma_load_im2col_4d(sa, &tmA1, &full[s], cb * BK, bw, bh, bn, (uint16_t)(rs % a.ks), (uint16_t)(rs / a.ks));
-            if (++cb == cblocks) { cb = 0; ++rs; }
+          if (CL == 2) {
+            // both CTAs' boxes complete on the leader's barrier, which expects the bytes of both
+            if (crank == 0) mbar_arrive_expect_tx(&full[s], 2 * C::kStageBytes);
+            const uint32_t lead = leader_addr(&full[s]);
+            if (IM2COL) {
+              tma_load_im2col_4d_pair(sa, &tmA1, lead, cb * BK, bw, bh, bn, (uint16_t)(rs % a.ks), (uint16_t)(rs / a.ks));
+              if (++cb == cblocks) { cb = 0; ++rs; }
+            } else {
+              tma_load_2d_pair(sa, k < a.K0 ? &tmA0 : &tmA1, lead, k, mt * BM);
+            }
+            tma_load_2d_pair(sa + C::kABytes, &tmB, lead, k, nt * BN + crank * (BN / 2));   // this CTA's half of the B tile
           } else {
-            tma_load_2d(sa, k < a.K0 ? &tmA0 : &tmA1, &full[s], k, mt * BM);
+            mbar_arrive_expect_tx(&full[s], C::kStageBytes);
+            if (IM2COL) {
+              tma_load_im2col_4d(sa, &tmA1, &full[s], cb * BK, bw, bh, bn, (uint16_t)(rs % a.ks), (uint16_t)(rs / a.ks));
+              if (++cb == cblocks) { cb = 0; ++rs; }
+            } else {
+              tma_load_2d(sa, k < a.K0 ? &tmA0 : &tmA1, &full[s], k, mt * BM);
+            }
+            tma_load_2d(sa + C::kABytes, &tmB, &full[s], k, nt * BN);
           }
-          tma_load_2d(sa + C::kABytes, &tmB, &full[s], k, nt * BN);
           if (++s == C::kStages) { s = 0; ph ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (all lanes run the loop, one elected lane issues: ptx.cuh) =====================
-    {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
+    if (CL == 1 || crank == 0) {                               // pair: the leader issues for both CTAs
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CL, BN, 0, 0);
       int s = 0;
       uint32_t ph = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      for (int tile = t_first; tile < t_limit; tile += t_step, ++it) {
         const int acc = it & 1;
         const uint32_t acc_ph = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_ph ^ 1);               // epilogue has drained this accumulator
+        mbar_wait(&tmem_empty[acc], acc_ph ^ 1);               // epilogue(s) have drained this accumulator
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < kblocks; ++kb) {
@@ -190,12 +222,19 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           const uint32_t sa = smem_u32(stage_base + (size_t)s * C::kStageBytes);
           // one descriptor per operand tile; a K step of 16 elements = 32 bytes = 2 units of the start-address field
           const uint64_t adesc = umma_smem_desc_sw128(sa, 0, 1024), bdesc = umma_smem_desc_sw128(sa + C::kABytes, 0, 1024);
+          if (CL == 2) {
 #pragma unroll
-          for (int kk = 0; kk < BK / 16; ++kk) umma_f16_elect(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (kb | kk) != 0);
-          umma_commit_elect(&empty[s]);                        // slot free once these MMAs have read it
+            for (int kk = 0; kk < BK / 16; ++kk) umma_f16_elect_pair(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (kb | kk) != 0);
+            umma_commit_elect_pair(&empty[s]);                 // both CTAs' producers may refill this stage
+          } else {
+#pragma unroll
+            for (int kk = 0; kk < BK / 16; ++kk) umma_f16_elect(d_tmem, adesc + 2u * kk, bdesc + 2u * kk, idesc, (kb | kk) != 0);
+            umma_commit_elect(&empty[s]);                      // slot free once these MMAs have read it
+          }
           if (++s == C::kStages) { s = 0; ph ^= 1; }
         }
-        umma_commit_elect(&tmem_full[acc]);                    // accumulator complete
+        if (CL == 2) umma_commit_elect_pair(&tmem_full[acc]);  // accumulator complete, in both CTAs
+        else umma_commit_elect(&tmem_full[acc]);
       }
     }
   } else {
@@ -217,8 +256,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
       if (blockIdx.x + gridDim.x < total_tiles) request_addend(blockIdx.x + gridDim.x, 1);
     }
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int mt = tile / a.n_tiles, nt = tile - mt * a.n_tiles;
+    for (int tile = t_first; tile < t_limit; tile += t_step, ++it) {
+      const int mt = (CL == 2 ? 2 : 1) * (tile / a.n_tiles) + crank, nt = tile % a.n_tiles;
       const int acc = it & 1;
       const uint32_t acc_ph = (it >> 1) & 1;
       const uint8_t* add_tile = RES ? addend + (size_t)acc * C::kStagingBytes : staging;
@@ -311,7 +350,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
           if (phase == 1) {                                      // TMEM accumulator fully read: hand it back to the MMA warp
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) { if (CL == 2) mbar_arrive_cluster(leader_addr(&tmem_empty[acc])); else mbar_arrive(&tmem_empty[acc]); }
           }
           fence_proxy_async_smem();                              // staging writes -> visible to the TMA engine
           named_bar_sync(1, kEpiThreads);
@@ -341,7 +380,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
         // TMEM accumulator fully read: hand it back to the MMA warp
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) { if (CL == 2) mbar_arrive_cluster(leader_addr(&tmem_empty[acc])); else mbar_arrive(&tmem_empty[acc]); }
         fence_proxy_async_smem();                                // staging writes -> visible to the TMA engine
         named_bar_sync(1, kEpiThreads);
         if (a.scat) {
@@ -415,9 +454,11 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();             // the peer may still be reading this CTA's shared memory / TMEM
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    if (CL == 2) tmem_dealloc_pair(tmem_base, C::kTmemCols);
+    else tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
@@ -430,20 +471,47 @@ int make_2d_map(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows,
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 }
 
-template <int BN, bool IM2COL, bool RES = false>
+// The CTA-pair mode pays where a CTA's L2 -> SM traffic is the bound: 256-wide N tiles with at least eight K blocks (measured:
+// 4-11 % faster from K = 512 on, 10-15 % SLOWER at K = 256, where the pair's extra synchronisation meets a short K loop --
+// profiles/r02_conv_halo.txt) and enough tile pairs to fill the GPU.  The caller must encode tmB with a HALF-tile box.
+inline bool pair_pays(long long M, int N, int K, int bn, bool im2col) {
+  if (option(OPT_GEMM_PAIR_OFF) || bn != 256 || K < 8 * BK) return false;
+  const long long m_tiles = (M + BM - 1) / BM;
+  if (im2col && (m_tiles & 1)) return false;                   // a tile past the last pixel would gather out-of-range windows
+  return ((m_tiles + 1) / 2) * (N / bn) >= num_sms() / 2;
+}
+
+template <int BN, bool IM2COL, bool RES = false, int CL = 1>
 int launch_kernel(const CUtensorMap& tmA0, const CUtensorMap& tmA1, const CUtensorMap& tmB, const CUtensorMap& tmD,
                   const CUtensorMap& tmR, GemmArgs a, cudaStream_t st) {
-  using C = Cfg<BN, RES>;
+  using C = Cfg<BN, RES, CL>;
   a.m_tiles = (int)((a.M + BM - 1) / BM);
   a.n_tiles = a.N / BN;
   static DevOnce once;
   if (once.pending()) {
-    MVFB_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, IM2COL, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+    MVFB_CUDA(cudaFuncSetAttribute(gemm_tn_kernel<BN, IM2COL, RES, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
     once.done();
+  }
+  if (CL == 2) {
+    int pairs = ((a.m_tiles + 1) / 2) * a.n_tiles;
+    if (pairs > num_sms() / 2) pairs = num_sms() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::kSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MVFB_CUDA(cudaLaunchKernelEx(&cfg, gemm_tn_kernel<BN, IM2COL, RES, CL>, tmA0, tmA1, tmB, tmD, tmR, a));
+    count_launch();
+    return MVFB_OK;
   }
   int grid = a.m_tiles * a.n_tiles;
   if (grid > num_sms()) grid = num_sms();
-  gemm_tn_kernel<BN, IM2COL, RES><<<grid, kThreads, C::kSmem, st>>>(tmA0, tmA1, tmB, tmD, tmR, a);
+  gemm_tn_kernel<BN, IM2COL, RES, CL><<<grid, kThreads, C::kSmem, st>>>(tmA0, tmA1, tmB, tmD, tmR, a);
   count_launch();
   MVFB_LAUNCH_CHECK();
   return MVFB_OK;
@@ -468,7 +536,8 @@ int launch(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* 
   } else {
     tmA0 = tmA1;
   }
-  if ((rc = make_2d_map(&tmB, b, (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldb, BK, BN))) return rc;
+  const bool pair = !RES && !res && pair_pays(d->M, d->N, d->K, BN, false);
+  if ((rc = make_2d_map(&tmB, b, (uint64_t)d->K, (uint64_t)d->N, (uint64_t)d->ldb, BK, pair ? BN / 2 : BN))) return rc;
   if ((rc = make_2d_map(&tmD, out, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)d->ldd, 64, BM))) return rc;
   tmR = tmD;
   if (RES && (rc = make_2d_map(&tmR, res, (uint64_t)d->N, (uint64_t)d->M, (uint64_t)ldr, 64, BM))) return rc;
@@ -480,6 +549,9 @@ int launch(const mvfb_gemm_desc* d, const void* a0, const void* a1, const void* 
   a.Cin = a.Ho = a.Wo = a.stride = a.pad = 0;
   a.ks = 1;
   a.scat = nullptr; a.scat_fill = 0;
+  if constexpr (BN == 256 && !RES) {
+    if (pair) return launch_kernel<BN, false, false, 2>(tmA0, tmA1, tmB, tmD, tmR, a, st);
+  }
   return launch_kernel<BN, false, RES>(tmA0, tmA1, tmB, tmD, tmR, a, st);
 }
 
@@ -498,7 +570,8 @@ int launch_conv3x3(const mvfb_conv_desc* d, const void* x, const void* w, void* 
                               CU_TENSOR_MAP_SWIZZLE_128B);
   if (rc) return rc;
   const long long M = (long long)d->F * Ho * Wo;
-  if ((rc = make_2d_map(&tmB, w, (uint64_t)taps * d->Cin, (uint64_t)d->Cout, (uint64_t)taps * d->Cin, BK, BN))) return rc;
+  const bool pair = !res && pair_pays(M, d->Cout, taps * d->Cin, BN, true);
+  if ((rc = make_2d_map(&tmB, w, (uint64_t)taps * d->Cin, (uint64_t)d->Cout, (uint64_t)taps * d->Cin, BK, pair ? BN / 2 : BN))) return rc;
   if ((rc = make_2d_map(&tmD, out, (uint64_t)d->Cout, (uint64_t)M, (uint64_t)d->Cout, 64, BM))) return rc;
   GemmArgs a;
   a.M = M; a.N = d->Cout; a.K = taps * d->Cin; a.K0 = 0;
@@ -507,6 +580,9 @@ int launch_conv3x3(const mvfb_conv_desc* d, const void* x, const void* w, void* 
   a.ep_scale = ep.scale; a.ep_shift = ep.shift; a.ep_relu = ep.relu;
   a.Cin = d->Cin; a.Ho = Ho; a.Wo = Wo; a.stride = d->stride; a.ks = d->ksize; a.pad = pad;
   a.scat = nullptr; a.scat_fill = 0;
+  if constexpr (BN == 256) {
+    if (pair) return launch_kernel<BN, true, false, 2>(tmA, tmA, tmB, tmD, tmD, a, st);
+  }
   return launch_kernel<BN, true>(tmA, tmA, tmB, tmD, tmD, a, st);
 }
 

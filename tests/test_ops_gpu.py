@@ -380,3 +380,25 @@ def test_conv_halo_matches_im2col_path_bit_for_bit_in_structure():
         _lib.set_option(_lib.OPT_CONV_HALO_OFF, 0)
     assert rel(y1, y2) < 4e-3 and not torch.isnan(y1.float()).any()
     assert rel(s1[0], s2[0]) < 2e-3 and rel(s1[1], s2[1]) < 1e-3
+
+
+@pytest.mark.parametrize("M,N,K,stats", [(9500, 512, 512, True), (25088, 1024, 512, True), (31000, 256, 1024, False), (9500, 768, 576, True)])
+def test_gemm_cta_pair_matches_single_cta(M, N, K, stats):
+    """Wide-N GEMMs launch as CTA pairs (tcgen05 cta_group::2: one M = 256 MMA over two CTAs, each holding half of the
+    weight tile; odd tile counts: the second CTA of the last pair works on rows past M, which TMA zero-fills and clips).
+    Same products, same accumulation order per output: bit-identical to the single-CTA launch, and both match fp32 torch."""
+    from mvfnet_b200 import ops, _lib
+    g = torch.Generator().manual_seed(M + N + K)
+    a = torch.randn((M, K), generator=g).cuda().bfloat16()
+    b = (torch.randn((N, K), generator=g) * 0.05).cuda().bfloat16()
+    out, cs, cq = ops.gemm_tn(a, b, stats=stats)
+    _lib.set_option(_lib.OPT_GEMM_PAIR_OFF, 1)
+    try:
+        ref, rs, rq = ops.gemm_tn(a, b, stats=stats)
+    finally:
+        _lib.set_option(_lib.OPT_GEMM_PAIR_OFF, 0)
+    assert torch.equal(out, ref)
+    f32 = a.float() @ b.float().t()
+    assert (out.float() - f32).abs().max().item() < 1e-2 * f32.abs().max().item()
+    if stats:
+        assert rel(cs, rs) < 1e-4 and rel(cq, rq) < 1e-5
