@@ -39,11 +39,11 @@ struct WArgs {
   int Ho, Wo, stride, ks, pad;     // IM2COL (3x3 / pad 1 or 1x1 / pad 0): output geometry; dw is (Cout, ks, ks, Cin)
 };
 
-template <int BN>
+template <int BN, int CL = 1>
 struct WCfg {
-  static constexpr int kStages = BN >= 256 ? 4 : 6;
+  static constexpr int kStages = (BN >= 256 && CL == 1) ? 4 : 6;
   static constexpr int kABytes = BM * BKP * 2;                // 2 boxes of 64 ch x 64 px
-  static constexpr int kBBytes = BN * BKP * 2;                // BN/64 boxes
+  static constexpr int kBBytes = BN * BKP * 2 / CL;           // BN/64 boxes; a CTA pair holds half of them each
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kTmemCols = BN < 32 ? 32 : BN;
   static constexpr size_t kSmem = 1024 + (size_t)kStages * kStageBytes + 256;
@@ -58,11 +58,13 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
-template <int BN, bool IM2COL>
+// CL = 2: CTA pairs (tcgen05 cta_group::2, as in gemm_tn.cu): the pair owns 256 output channels of one (cin tile, pixel range)
+// work item; each CTA loads its own 128 dY columns and HALF of the X tile, the leader issues M = 256 MMAs.
+template <int BN, bool IM2COL, int CL = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant__ CUtensorMap tmX0,
                   const __grid_constant__ CUtensorMap tmX1, const WArgs a) {
-  using C = WCfg<BN>;
+  using C = WCfg<BN, CL>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)C::kStages * C::kStageBytes);
@@ -74,9 +76,11 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // work item -> (cout tile, cin tile, pixel range).  Tiles vary fastest so that co-resident CTAs work on the SAME
   // pixel range: the dY / X blocks they share (all 9 filter taps, all channel tiles) are then served by L2.
-  const int ntile_all = a.n_tiles * a.k_tiles;
-  const int split = blockIdx.x / ntile_all, tile = blockIdx.x - split * ntile_all;
-  const int nt = tile / a.k_tiles, kt = tile - nt * a.k_tiles;
+  const int crank = CL == 2 ? (int)cluster_ctarank() : 0;
+  const int item = (int)blockIdx.x / CL;                          // work item of this CTA (pair)
+  const int ntile_all = (a.n_tiles / CL) * a.k_tiles;
+  const int split = item / ntile_all, tile = item - split * ntile_all;
+  const int nt = CL * (tile / a.k_tiles) + crank, kt = tile % a.k_tiles;
   // IM2COL: kt enumerates (filter tap rs, channel tile ct); the tap's input pixels are gathered by TMA im2col
   const int ctiles = (a.K + BN - 1) / BN;                      // the last tile may run past K: TMA zero-fills, the epilogue skips
   const int rs = IM2COL ? kt / ctiles : 0, ct = IM2COL ? kt - rs * ctiles : kt;
@@ -98,11 +102,16 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, C::kTmemCols);
-    tmem_relinquish();
+    if (CL == 2) {
+      tmem_alloc_pair(tmem_slot, C::kTmemCols);
+    } else {
+      tmem_alloc(tmem_slot, C::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -113,30 +122,43 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
       for (int i = 0; i < nblocks; ++i) {
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t* sa = smem + (size_t)s * C::kStageBytes;
-        mbar_arrive_expect_tx(&full[s], C::kStageBytes);
         const int p = (pb0 + i) * BKP;
-#pragma unroll
-        for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BKP * 128), &tmG, &full[s], nt * BM + j * 64, p);
+        int bw = 0, bh = 0, bn = 0;
         if (IM2COL) {
           const int q = p % a.Wo, pq = p / a.Wo;                // first output pixel of the block -> window origin
-          const int bw = q * a.stride - a.pad, bh = (pq % a.Ho) * a.stride - a.pad, bn = pq / a.Ho;
+          bw = q * a.stride - a.pad; bh = (pq % a.Ho) * a.stride - a.pad; bn = pq / a.Ho;
+        }
+        if (CL == 2) {
+          // both CTAs' boxes complete on the leader's barrier, which expects the bytes of both
+          if (crank == 0) mbar_arrive_expect_tx(&full[s], 2 * C::kStageBytes);
+          const uint32_t lead = leader_addr(&full[s]);
 #pragma unroll
-          for (int j = 0; j < BN / 64; ++j)
-            tma_load_im2col_4d(sa + C::kABytes + j * (BKP * 128), &tmX1, &full[s], ct * BN + j * 64, bw, bh, bn,
-                               (uint16_t)(rs % a.ks), (uint16_t)(rs / a.ks));
+          for (int j = 0; j < BM / 64; ++j) tma_load_2d_pair(sa + j * (BKP * 128), &tmG, lead, nt * BM + j * 64, p);
+#pragma unroll
+          for (int j = 0; j < BN / 128; ++j) {                    // this CTA's half of the X tile
+            const int c = ct * BN + crank * (BN / 2) + j * 64;
+            if (IM2COL) tma_load_im2col_4d_pair(sa + C::kABytes + j * (BKP * 128), &tmX1, lead, c, bw, bh, bn,
+                                                (uint16_t)(rs % a.ks), (uint16_t)(rs / a.ks));
+            else tma_load_2d_pair(sa + C::kABytes + j * (BKP * 128), c < a.K0 ? &tmX0 : &tmX1, lead, c, p);
+          }
         } else {
+          mbar_arrive_expect_tx(&full[s], C::kStageBytes);
+#pragma unroll
+          for (int j = 0; j < BM / 64; ++j) tma_load_2d(sa + j * (BKP * 128), &tmG, &full[s], nt * BM + j * 64, p);
 #pragma unroll
           for (int j = 0; j < BN / 64; ++j) {
             const int c = ct * BN + j * 64;
-            tma_load_2d(sa + C::kABytes + j * (BKP * 128), c < a.K0 ? &tmX0 : &tmX1, &full[s], c, p);
+            if (IM2COL) tma_load_im2col_4d(sa + C::kABytes + j * (BKP * 128), &tmX1, &full[s], c, bw, bh, bn,
+                                           (uint16_t)(rs % a.ks), (uint16_t)(rs / a.ks));
+            else tma_load_2d(sa + C::kABytes + j * (BKP * 128), c < a.K0 ? &tmX0 : &tmX1, &full[s], c, p);
           }
         }
         if (++s == C::kStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    {                                                          // all lanes run the loop, one elected lane issues (ptx.cuh)
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 1, 1);      // both operands MN-major
+    if (CL == 1 || crank == 0) {                               // all lanes run the loop, one elected lane issues (ptx.cuh)
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CL, BN, 1, 1);   // both operands MN-major
       int s = 0;
       uint32_t ph = 0;
       for (int i = 0; i < nblocks; ++i) {
@@ -144,13 +166,21 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
         tc_fence_after();
         const uint32_t sa = smem_u32(smem + (size_t)s * C::kStageBytes);
         const uint64_t adesc = desc_mn_sw128(sa), bdesc = desc_mn_sw128(sa + C::kABytes);
+        if (CL == 2) {
 #pragma unroll
-        for (int kk = 0; kk < BKP / 16; ++kk)                   // 16 pixels = 2 atoms = 2048 bytes = 128 descriptor units
-          umma_f16_elect(tmem_base, adesc + 128u * kk, bdesc + 128u * kk, idesc, (i | kk) != 0);
-        umma_commit_elect(&empty[s]);
+          for (int kk = 0; kk < BKP / 16; ++kk)
+            umma_f16_elect_pair(tmem_base, adesc + 128u * kk, bdesc + 128u * kk, idesc, (i | kk) != 0);
+          umma_commit_elect_pair(&empty[s]);
+        } else {
+#pragma unroll
+          for (int kk = 0; kk < BKP / 16; ++kk)                 // 16 pixels = 2 atoms = 2048 bytes = 128 descriptor units
+            umma_f16_elect(tmem_base, adesc + 128u * kk, bdesc + 128u * kk, idesc, (i | kk) != 0);
+          umma_commit_elect(&empty[s]);
+        }
         if (++s == C::kStages) { s = 0; ph ^= 1; }
       }
-      umma_commit_elect(done);
+      if (CL == 2) umma_commit_elect_pair(done);
+      else umma_commit_elect(done);
     }
   } else if (nblocks > 0) {
     // epilogue: TMEM -> registers -> fp32 atomics on dW (rows = output channels of this tile)
@@ -177,9 +207,11 @@ gemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmG, const __grid_constant
 
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    if (CL == 2) tmem_dealloc_pair(tmem_base, C::kTmemCols);
+    else tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
@@ -191,10 +223,37 @@ int map_64x64(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, u
                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
 }
 
+template <int BN, bool IM2COL, int CL>
+int launch_wgrad_grid(const CUtensorMap& tmG, const CUtensorMap& tmX0, const CUtensorMap& tmX1, const WArgs& a, int ctas,
+                      cudaStream_t st) {
+  using C = WCfg<BN, CL>;
+  static DevOnce once;
+  if (once.pending()) {
+    MVFB_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel<BN, IM2COL, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
+    once.done();
+  }
+  if (CL == 2) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::kSmem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MVFB_CUDA(cudaLaunchKernelEx(&cfg, gemm_wgrad_kernel<BN, IM2COL, CL>, tmG, tmX0, tmX1, a));
+    return MVFB_OK;
+  }
+  gemm_wgrad_kernel<BN, IM2COL, CL><<<ctas, kThreads, C::kSmem, st>>>(tmG, tmX0, tmX1, a);
+  MVFB_LAUNCH_CHECK();
+  return MVFB_OK;
+}
+
 template <int BN, bool IM2COL>
 int launch_wgrad_kernel(const CUtensorMap& tmG, const CUtensorMap& tmX0, const CUtensorMap& tmX1, WArgs a, size_t dw_elems,
                         cudaStream_t st) {
-  using C = WCfg<BN>;
   a.n_tiles = (a.N + BM - 1) / BM;
   a.k_tiles = ((a.K + BN - 1) / BN) * (IM2COL ? a.ks * a.ks : 1);
   a.pblocks = (int)((a.M + BKP - 1) / BKP);
@@ -203,15 +262,17 @@ int launch_wgrad_kernel(const CUtensorMap& tmG, const CUtensorMap& tmX0, const C
   if (splits > a.pblocks) splits = a.pblocks;
   if (splits < 1) splits = 1;
   a.splits = splits;
-  static DevOnce once;
-  if (once.pending()) {
-    MVFB_CUDA(cudaFuncSetAttribute(gemm_wgrad_kernel<BN, IM2COL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmem));
-    once.done();
-  }
   MVFB_CUDA(cudaMemsetAsync(a.dw, 0, sizeof(float) * dw_elems, st));
-  gemm_wgrad_kernel<BN, IM2COL><<<tiles * splits, kThreads, C::kSmem, st>>>(tmG, tmX0, tmX1, a);
+  // CTA pairs: 256 output channels per work item, half of the X tile per CTA (same condition as gemm_tn.cu's pairs: wide
+  // tiles, whole 256-channel pairs, a reduction long enough to pay for the pair's synchronisation)
+  int rc;
+  if (BN == 256 && a.K % 256 == 0 && a.N % 256 == 0 && option(OPT_GEMM_PAIR_OFF) == 0 && a.pblocks / splits >= 8) {
+    rc = launch_wgrad_grid<BN, IM2COL, 2>(tmG, tmX0, tmX1, a, tiles * splits, st);
+  } else {
+    rc = launch_wgrad_grid<BN, IM2COL, 1>(tmG, tmX0, tmX1, a, tiles * splits, st);
+  }
+  if (rc) return rc;
   count_launch();
-  MVFB_LAUNCH_CHECK();
   return MVFB_OK;
 }
 
