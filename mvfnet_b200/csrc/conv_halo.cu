@@ -25,8 +25,10 @@ constexpr int BK = 64;
 constexpr int kEpiWarps = 8;
 constexpr int kEpiThreads = 32 * kEpiWarps;
 constexpr int kThreads = 64 + kEpiThreads;
-constexpr int kMaxBands = 4;
+constexpr int kMaxBands = 4;        // deeper rings (3 bands + 14 weight stages, 2 + 16) measured the same: r02_conv_halo.txt
 constexpr int kMaxBStages = 8;
+constexpr int kBarBytes = 512;      // barriers + the TMEM address slot
+static_assert((2 * kMaxBands + 2 * kMaxBStages + 4) * 8 + 4 <= kBarBytes, "barrier area");
 
 struct HaloArgs {
   int F, H, W, Cin, Cout;
@@ -44,10 +46,14 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int BN>
+// CL = 2: a CTA pair (cluster of two, tcgen05 cta_group::2) works on two consecutive tiles of the same output-channel
+// tile: each CTA stages its own band and HALF of every weight tile, the leader (cluster rank 0) issues M = 256 MMAs over
+// both CTAs' shared memory (gemm_tn.cu's pair mode).  For the streamed-weight case (C = 128) that halves the weight
+// bytes each SM pulls per tile -- 288 of the 334 KB a tile needs.
+template <int BN, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmB, const HaloArgs a) {
-  constexpr int kBBytes = BN * BK * 2;                         // one (tap, channel block) weight tile
+  constexpr int kBBytes = BN * BK * 2 / CL;                    // this CTA's part of one (tap, channel block) weight tile
   constexpr int kStagingBytes = BM * BN * 2;
   constexpr int kPanels = BN / 64;
   constexpr int kTmemCols = 2 * BN;
@@ -66,11 +72,15 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   uint64_t* tmem_full = b_empty + kMaxBStages;                 // [2]
   uint64_t* tmem_empty = tmem_full + 2;                        // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  long long* s_rowoff2 = reinterpret_cast<long long*>(tail + 256);             // [2][BM]: tile i uses half i & 1
-  float* s_stat = reinterpret_cast<float*>(tail + 256 + 2 * BM * 8);           // [kStatParts][2][BN]
+  long long* s_rowoff2 = reinterpret_cast<long long*>(tail + kBarBytes);             // [2][BM]: tile i uses half i & 1
+  float* s_stat = reinterpret_cast<float*>(tail + kBarBytes + 2 * BM * 8);           // [kStatParts][2][BN]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_tiles = a.m_tiles * a.n_tiles;
+  const int crank = CL == 2 ? (int)cluster_ctarank() : 0;
+  const int t_first = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_step = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int t_limit = CL == 2 ? ((a.m_tiles + 1) / 2) * a.n_tiles : total_tiles;   // pair: work items of two M tiles
   const uint32_t band_tx = (uint32_t)((a.R + 2) * a.Wp * 128);
 
   if (threadIdx.x == 0) {
@@ -78,22 +88,29 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < kMaxBands; ++s) { mbar_init(&band_full[s], 1); mbar_init(&band_empty[s], 1); }
     for (int s = 0; s < kMaxBStages; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], kEpiThreads / 32); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], (kEpiThreads / 32) * CL); }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, kTmemCols);
-    tmem_relinquish();
+    if (CL == 2) {
+      tmem_alloc_pair(tmem_slot, kTmemCols);
+    } else {
+      tmem_alloc(tmem_slot, kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();             // the peer's barriers exist before anything is sent to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // tile -> (output-channel tile, frame, first image row)
+  // work item -> (output-channel tile, frame, first image row); the odd CTA of a pair may get f == F (nothing to do: its
+  // band is TMA's zero fill and its rows are all "padding")
   auto tile_geo = [&](int tile, int& nt, int& f, int& h0) {
-    const int mt = tile / a.n_tiles;
-    nt = tile - mt * a.n_tiles;
+    const int q = tile / a.n_tiles;
+    const int mt = CL * q + crank;
+    nt = tile - q * a.n_tiles;
     f = mt / a.tiles_per_frame;
     h0 = a.R * (mt - f * a.tiles_per_frame);
   };
@@ -101,25 +118,36 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      if (a.bres && (int)blockIdx.x < total_tiles) {           // the whole weight matrix, once
+      if (CL == 1 && a.bres && (int)blockIdx.x < total_tiles) {   // the whole weight matrix, once
         mbar_arrive_expect_tx(&b_full[0], (uint32_t)(9 * a.cblocks * kBBytes));
         for (int kb = 0; kb < 9 * a.cblocks; ++kb) tma_load_2d(b_base + (size_t)kb * kBBytes, &tmB, &b_full[0], kb * BK, 0);
       }
       int bs = 0, ss = 0;
       uint32_t bph = 0, sph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      for (int tile = t_first; tile < t_limit; tile += t_step) {
         int nt, f, h0;
         tile_geo(tile, nt, f, h0);
         for (int cb = 0; cb < a.cblocks; ++cb) {
           mbar_wait(&band_empty[bs], bph ^ 1);
-          mbar_arrive_expect_tx(&band_full[bs], band_tx);
-          tma_load_4d(band_base + (size_t)bs * a.band_bytes, &tmX, &band_full[bs], cb * BK, -1, h0 - 1, f);
+          if (CL == 2) {                                       // both CTAs' boxes complete on the leader's barrier
+            if (crank == 0) mbar_arrive_expect_tx(&band_full[bs], 2 * band_tx);
+            tma_load_4d_pair(band_base + (size_t)bs * a.band_bytes, &tmX, leader_addr(&band_full[bs]), cb * BK, -1, h0 - 1, f);
+          } else {
+            mbar_arrive_expect_tx(&band_full[bs], band_tx);
+            tma_load_4d(band_base + (size_t)bs * a.band_bytes, &tmX, &band_full[bs], cb * BK, -1, h0 - 1, f);
+          }
           if (++bs == a.bands) { bs = 0; bph ^= 1; }
-          if (!a.bres) {
+          if (CL == 2 || !a.bres) {
             for (int tap = 0; tap < 9; ++tap) {
               mbar_wait(&b_empty[ss], sph ^ 1);
-              mbar_arrive_expect_tx(&b_full[ss], kBBytes);
-              tma_load_2d(b_base + (size_t)ss * kBBytes, &tmB, &b_full[ss], tap * a.Cin + cb * BK, nt * BN);
+              if (CL == 2) {                                   // this CTA's half of the weight tile's output channels
+                if (crank == 0) mbar_arrive_expect_tx(&b_full[ss], 2 * kBBytes);
+                tma_load_2d_pair(b_base + (size_t)ss * kBBytes, &tmB, leader_addr(&b_full[ss]), tap * a.Cin + cb * BK,
+                                 nt * BN + crank * (BN / 2));
+              } else {
+                mbar_arrive_expect_tx(&b_full[ss], kBBytes);
+                tma_load_2d(b_base + (size_t)ss * kBBytes, &tmB, &b_full[ss], tap * a.Cin + cb * BK, nt * BN);
+              }
               if (++ss == a.bstages) { ss = 0; sph ^= 1; }
             }
           }
@@ -128,17 +156,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    {
-      constexpr uint32_t idesc = umma_idesc_bf16(BM, BN, 0, 0);
-      if (a.bres && (int)blockIdx.x < total_tiles) {
+    if (CL == 1 || crank == 0) {                               // pair: the leader issues for both CTAs
+      constexpr uint32_t idesc = umma_idesc_bf16(BM * CL, BN, 0, 0);
+      const bool bres = CL == 1 && a.bres;
+      if (bres && (int)blockIdx.x < total_tiles) {
         mbar_wait(&b_full[0], 0);
         tc_fence_after();
       }
       int bs = 0, ss = 0, it = 0;
       uint32_t bph = 0, sph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-        int nt, f, h0;
-        tile_geo(tile, nt, f, h0);
+      for (int tile = t_first; tile < t_limit; tile += t_step, ++it) {
         const int acc = it & 1;
         mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
         tc_fence_after();
@@ -158,24 +185,32 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
             const int r = tap / 3, s = tap - 3 * r;
             const uint64_t ad = a_first + (uint64_t)(uint32_t)((r * a.Wp + s) * 8);   // a row of 128 bytes = 8 descriptor units
             uint64_t bd;
-            if (a.bres) {
+            if (bres) {
               bd = b_res + (uint64_t)(uint32_t)(tap * a.cblocks * (kBBytes / 16));
             } else {
               mbar_wait(&b_full[ss], sph);
               tc_fence_after();
               bd = umma_smem_desc_sw128(smem_u32(b_base) + (uint32_t)ss * kBBytes, 0, 1024);
             }
+            if (CL == 2) {
 #pragma unroll
-            for (int kk = 0; kk < BK / 16; ++kk) umma_f16_elect(d_tmem, ad + 2u * kk, bd + 2u * kk, idesc, (cb | tap | kk) != 0);
-            if (!a.bres) {
-              umma_commit_elect(&b_empty[ss]);
+              for (int kk = 0; kk < BK / 16; ++kk) umma_f16_elect_pair(d_tmem, ad + 2u * kk, bd + 2u * kk, idesc, (cb | tap | kk) != 0);
+              umma_commit_elect_pair(&b_empty[ss]);                  // both CTAs' producers may refill this stage
               if (++ss == a.bstages) { ss = 0; sph ^= 1; }
+            } else {
+#pragma unroll
+              for (int kk = 0; kk < BK / 16; ++kk) umma_f16_elect(d_tmem, ad + 2u * kk, bd + 2u * kk, idesc, (cb | tap | kk) != 0);
+              if (!bres) {
+                umma_commit_elect(&b_empty[ss]);
+                if (++ss == a.bstages) { ss = 0; sph ^= 1; }
+              }
             }
           }
-          umma_commit_elect(&band_empty[bs]);                        // the band is free once these MMAs have read it
+          // the band (both CTAs' in a pair) is free once these MMAs have read it
+          if (CL == 2) umma_commit_elect_pair(&band_empty[bs]); else umma_commit_elect(&band_empty[bs]);
           if (++bs == a.bands) { bs = 0; bph ^= 1; }
         }
-        umma_commit_elect(&tmem_full[acc]);
+        if (CL == 2) umma_commit_elect_pair(&tmem_full[acc]); else umma_commit_elect(&tmem_full[acc]);
       }
     }
   } else {
@@ -185,8 +220,30 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
     const int half = (warp - 2) >> 2;
     const int row = lane_grp * 32 + lane;
     constexpr int kHalfN = BN / 2;
+    // Per-column sums of the rounded tiles (gemm_tn.cu's scheme), kept in registers ACROSS the CTA's tiles: thread
+    // (pair, part) owns two columns and every kStatParts-th block of rows; one shared-memory reduction and one atomic
+    // per column when the output-channel tile changes (never, for the one-tile widths of layer1/2) and at the end.
+    constexpr int kPairs = BN / 2;
+    constexpr int kRows = BM / kStatParts;
+    const int st_pair = et % kPairs, st_part = et / kPairs;
+    float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
+    int stat_nt = -1;
+    auto flush_stats = [&](int nt_of) {
+      float* mine = s_stat + (size_t)st_part * (2 * BN);
+      *reinterpret_cast<float2*>(mine + 2 * st_pair) = make_float2(s1a, s1b);
+      *reinterpret_cast<float2*>(mine + BN + 2 * st_pair) = make_float2(s2a, s2b);
+      named_bar_sync(2, kEpiThreads);
+      for (int i = et; i < 2 * BN; i += kEpiThreads) {
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < kStatParts; ++q) v += s_stat[(size_t)q * (2 * BN) + i];
+        atomicAdd(i < BN ? &a.colsum[nt_of * BN + i] : &a.colsq[nt_of * BN + i - BN], v);
+      }
+      named_bar_sync(2, kEpiThreads);
+      s1a = s1b = s2a = s2b = 0.f;
+    };
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    for (int tile = t_first; tile < t_limit; tile += t_step, ++it) {
       int nt, f, h0;
       tile_geo(tile, nt, f, h0);
       const int acc = it & 1;
@@ -196,7 +253,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
         const int j = et + 1;                                  // position within the tile's first padded row, from column 0
         const int dh = j / a.Wp, wp = j - dh * a.Wp;
         long long off = -1;
-        if (wp >= 1 && wp <= a.W && dh < a.R && h0 + dh < a.H) off = (((long long)f * a.H + (h0 + dh)) * a.W + (wp - 1)) * a.Cout;
+        if (wp >= 1 && wp <= a.W && dh < a.R && h0 + dh < a.H && f < a.F) off = (((long long)f * a.H + (h0 + dh)) * a.W + (wp - 1)) * a.Cout;
         s_rowoff[et] = off;
       }
       named_bar_sync(1, kEpiThreads);                          // offsets visible; the previous tile's staging reads are over
@@ -226,7 +283,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) { if (CL == 2) mbar_arrive_cluster(leader_addr(&tmem_empty[acc])); else mbar_arrive(&tmem_empty[acc]); }
       named_bar_sync(1, kEpiThreads);
       // store: 16-byte chunks, a warp covers whole rows
       {
@@ -242,45 +299,36 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant_
           }
         }
       }
-      if (a.colsum) {                                          // per-column sums of the rounded tile (gemm_tn.cu's scheme)
-        constexpr int kPairs = BN / 2;
-        constexpr int kRows = BM / kStatParts;
-        {
-          const int pair = et % kPairs, part = et / kPairs;
-          const int col = 2 * pair;
-          const uint8_t* panel = staging + (size_t)(col >> 6) * (BM * 128);
-          const int chunk = (col & 63) >> 3, within = (col & 7) * 2;
-          float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f;
-#pragma unroll 8
-          for (int rr = 0; rr < kRows; ++rr) {
-            const int r = part * kRows + rr;
-            const uint32_t h2 = *reinterpret_cast<const uint32_t*>(panel + r * 128 + ((chunk ^ (r & 7)) << 4) + within);
-            bf16x2_sum_sq(h2, s1a, s1b, s2a, s2b);
-          }
-          float* mine = s_stat + (size_t)part * (2 * BN);
-          *reinterpret_cast<float2*>(mine + col) = make_float2(s1a, s1b);
-          *reinterpret_cast<float2*>(mine + BN + col) = make_float2(s2a, s2b);
+      if (a.colsum) {
+        if (nt != stat_nt) {
+          if (stat_nt >= 0) flush_stats(stat_nt);
+          stat_nt = nt;
         }
-        named_bar_sync(1, kEpiThreads);
-        for (int i = et; i < 2 * BN; i += kEpiThreads) {
-          float v = 0.f;
-#pragma unroll
-          for (int q = 0; q < kStatParts; ++q) v += s_stat[(size_t)q * (2 * BN) + i];
-          atomicAdd(i < BN ? &a.colsum[nt * BN + i] : &a.colsq[nt * BN + i - BN], v);
+        const int col = 2 * st_pair;
+        const uint8_t* panel = staging + (size_t)(col >> 6) * (BM * 128);
+        const int chunk = (col & 63) >> 3, within = (col & 7) * 2;
+#pragma unroll 8
+        for (int rr = 0; rr < kRows; ++rr) {
+          const int r = st_part * kRows + rr;
+          const uint32_t h2 = *reinterpret_cast<const uint32_t*>(panel + r * 128 + ((chunk ^ (r & 7)) << 4) + within);
+          bf16x2_sum_sq(h2, s1a, s1b, s2a, s2b);
         }
       }
     }
+    if (a.colsum && stat_nt >= 0) flush_stats(stat_nt);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();             // the peer may still be reading this CTA's shared memory / TMEM
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, kTmemCols);
+    if (CL == 2) tmem_dealloc_pair(tmem_base, kTmemCols);
+    else tmem_dealloc(tmem_base, kTmemCols);
   }
 }
 
-template <int BN>
+template <int BN, int CL>
 int launch_halo(const mvfb_conv_desc* d, const void* x, const void* w, void* out, float* colsum, float* colsq, cudaStream_t st) {
   HaloArgs a;
   a.F = d->F; a.H = d->H; a.W = d->W; a.Cin = d->Cin; a.Cout = d->Cout;
@@ -293,13 +341,13 @@ int launch_halo(const mvfb_conv_desc* d, const void* x, const void* w, void* out
   a.band_bytes = (((2 * a.Wp + 2 + BM) * 128 + 1023) / 1024) * 1024;
   a.colsum = colsum; a.colsq = colsq;
   a.out = (__nv_bfloat16*)out;
-  constexpr int kBBytes = BN * BK * 2;
-  const size_t fixed = 1024 + (size_t)BM * BN * 2 + 256 + 2 * BM * 8 + (size_t)(kEpiThreads / (BN / 2)) * BN * 2 * 4;
+  constexpr int kBBytes = BN * BK * 2 / CL;
+  const size_t fixed = 1024 + (size_t)BM * BN * 2 + kBarBytes + 2 * BM * 8 + (size_t)(kEpiThreads / (BN / 2)) * BN * 2 * 4;
   const size_t budget = 227 * 1024;
   // weights resident when they fit beside two bands; otherwise a ring of (tap, channel block) tiles
   a.bres = 0;
   const size_t wbytes = (size_t)9 * a.cblocks * kBBytes;
-  if (a.n_tiles == 1 && fixed + wbytes + 2 * (size_t)a.band_bytes <= budget) a.bres = 1;
+  if (CL == 1 && a.n_tiles == 1 && fixed + wbytes + 2 * (size_t)a.band_bytes <= budget) a.bres = 1;
   const size_t bsm = a.bres ? wbytes : 0;
   a.bstages = a.bres ? 0 : 6;
   size_t left = budget - fixed - bsm - (a.bres ? 0 : (size_t)a.bstages * kBBytes);
@@ -322,18 +370,35 @@ int launch_halo(const mvfb_conv_desc* d, const void* x, const void* w, void* out
   if (rc) return rc;
   const uint64_t bdims[2] = {(uint64_t)9 * d->Cin, (uint64_t)d->Cout};
   const uint64_t bstrides[1] = {(uint64_t)9 * d->Cin * 2};
-  const uint32_t bbox[2] = {(uint32_t)BK, (uint32_t)BN};
+  const uint32_t bbox[2] = {(uint32_t)BK, (uint32_t)(BN / CL)};
   rc = encode_tmap(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w, bdims, bstrides, bbox, nullptr, CU_TENSOR_MAP_SWIZZLE_128B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
   if (rc) return rc;
   static DevOnce once;
   if (once.pending()) {
-    MVFB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    MVFB_CUDA(cudaFuncSetAttribute(conv_halo_kernel<BN, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     once.done();
+  }
+  if (CL == 2) {
+    int pairs = ((a.m_tiles + 1) / 2) * a.n_tiles;
+    if (pairs > num_sms() / 2) pairs = num_sms() / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MVFB_CUDA(cudaLaunchKernelEx(&cfg, conv_halo_kernel<BN, CL>, tmX, tmB, a));
+    count_launch();
+    return MVFB_OK;
   }
   int grid = a.m_tiles * a.n_tiles;
   if (grid > num_sms()) grid = num_sms();
-  conv_halo_kernel<BN><<<grid, kThreads, smem_bytes, st>>>(tmX, tmB, a);
+  conv_halo_kernel<BN, CL><<<grid, kThreads, smem_bytes, st>>>(tmX, tmB, a);
   count_launch();
   MVFB_LAUNCH_CHECK();
   return MVFB_OK;
@@ -352,8 +417,13 @@ bool conv_halo_eligible(const mvfb_conv_desc* d) {
 }
 
 int conv_halo(const mvfb_conv_desc* d, const void* x, const void* w, void* out, float* colsum, float* colsq, cudaStream_t st) {
-  if (d->Cout % 128 == 0) return launch_halo<128>(d, x, w, out, colsum, colsq, st);
-  return launch_halo<64>(d, x, w, out, colsum, colsq, st);
+  if (d->Cout % 128 == 0) {
+    // streamed weights: a CTA pair halves the weight bytes per SM -- 243 vs 271 us at C = 128 / 28x28 / 1280 frames;
+    // with one channel block (nine k-blocks per tile) the pair's synchronisation costs more: 169 vs 151 us
+    if (option(OPT_GEMM_PAIR_OFF) == 0 && d->Cin >= 2 * BK) return launch_halo<128, 2>(d, x, w, out, colsum, colsq, st);
+    return launch_halo<128, 1>(d, x, w, out, colsum, colsq, st);
+  }
+  return launch_halo<64, 1>(d, x, w, out, colsum, colsq, st);
 }
 
 }  // namespace mvfb

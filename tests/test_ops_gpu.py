@@ -167,7 +167,10 @@ def test_fused_bottleneck_vs_torch_fp32(inpl, planes, hw, stride, mvf, monkeypat
                                                  (40, 64, 64, 56, 1), (100, 128, 128, 56, 2),
                                                  # the halo-band kernel (conv_halo.cu): weights resident / streamed, one and
                                                  # two channel blocks, a frame height whose last tile is mostly padding
-                                                 (60, 128, 128, 28, 1), (50, 64, 128, 28, 1), (40, 128, 64, 56, 1), (90, 64, 64, 30, 1)])
+                                                 (60, 128, 128, 28, 1), (50, 64, 128, 28, 1), (40, 128, 64, 56, 1), (90, 64, 64, 30, 1),
+                                                 # CTA pairs in the halo kernel: an odd tile count (the last pair's second
+                                                 # CTA has no frame), two output-channel tiles
+                                                 (61, 128, 128, 28, 1), (45, 128, 256, 28, 1)])
 def test_conv3x3_implicit_gemm(F, Cin, Cout, H, stride):
     """TMA-im2col implicit GEMM vs torch conv2d in fp32 on the same bf16-rounded operands; forward, fused statistics,
     and the stride-1 input gradient (rotated weights through the same kernel)."""
@@ -380,6 +383,28 @@ def test_conv_halo_matches_im2col_path_bit_for_bit_in_structure():
         _lib.set_option(_lib.OPT_CONV_HALO_OFF, 0)
     assert rel(y1, y2) < 4e-3 and not torch.isnan(y1.float()).any()
     assert rel(s1[0], s2[0]) < 2e-3 and rel(s1[1], s2[1]) < 1e-3
+
+
+@pytest.mark.parametrize("F,Cin,Cout,H", [(61, 128, 128, 28), (45, 128, 256, 28), (50, 64, 128, 28), (160, 128, 128, 14)])
+def test_conv_halo_cta_pair_matches_single_cta(F, Cin, Cout, H):
+    """The halo kernel's CTA-pair mode (streamed weights, half of each weight tile per CTA, M = 256 MMAs issued by the
+    leader) computes every output with the same products in the same order as the single-CTA launch: bit-identical
+    outputs; the fused statistics differ only by the order of the atomics."""
+    from mvfnet_b200 import ops, _lib
+    g = torch.Generator(device="cuda").manual_seed(F + Cin + Cout)
+    x = torch.randn(F, Cin, H, H, device="cuda", generator=g).bfloat16().contiguous(memory_format=torch.channels_last)
+    w = (torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) / (3 * Cin ** 0.5)).bfloat16().permute(0, 2, 3, 1).contiguous()
+    y1, s1 = ops.conv3x3_raw(x, w, 1, stats=True)
+    _lib.set_option(_lib.OPT_GEMM_PAIR_OFF, 1)
+    try:
+        y2, s2 = ops.conv3x3_raw(x, w, 1, stats=True)
+    finally:
+        _lib.set_option(_lib.OPT_GEMM_PAIR_OFF, 0)
+    assert torch.equal(y1, y2) and not torch.isnan(y1.float()).any()
+    assert rel(s1[0], s2[0]) < 1e-4 or float((s1[0] - s2[0]).abs().max()) < 1e-3 * float(y1.float().abs().sum((0, 2, 3)).max())
+    assert rel(s1[1], s2[1]) < 1e-5
+    ref = torch.nn.functional.conv2d(x.float(), w.permute(0, 3, 1, 2).float(), None, 1, 1)
+    assert rel(y1, ref) < 1e-2
 
 
 @pytest.mark.parametrize("M,N,K,stats", [(9500, 512, 512, True), (25088, 1024, 512, True), (31000, 256, 1024, False), (9500, 768, 576, True)])
