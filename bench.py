@@ -32,8 +32,11 @@ METRIC = "clips/sec (fwd+bwd) MVFNet-R50 8x8 224px"
 T_FRAMES, PX, DEPTH = 8, 224, 50
 # dram__bytes_read.sum + dram__bytes_write.sum of the train-mode mvf_sweep_kernel launch over its algorithmic bytes, from
 # the `ncu --set full` capture of THIS build named below (per launch, like `achieved`); None = not captured
-MVF_FWD_TRAFFIC_RATIO = None
-MVF_FWD_TRAFFIC_SOURCE = None
+MVF_FWD_TRAFFIC_RATIO = (80.195328 + 17.586176) / 128.45
+MVF_FWD_TRAFFIC_SOURCE = ("profiles/r02_mvf_sweep_fwd_ncu.csv (ncu --set full, mvf_sweep_kernel<2, 8, 1>, B = 160 clips, 14x14 slab of "
+                          "32.1 M elements: dram read 80.2 MB + write 17.6 MB per launch against 128.5 MB algorithmic -- the second sweep "
+                          "reads the slab from L2 and part of the output is still in the 126 MB L2 when the launch ends); scaled to "
+                          "this run's mean algorithmic bytes per launch")
 
 
 def model_cfg(depth=DEPTH, t=T_FRAMES, dropout=0.5):
