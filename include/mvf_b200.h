@@ -284,6 +284,25 @@ int stem_im2col(const void* x, void* a, long long F, int H, int W, mvfb_stream_t
 int maxpool3x3s2_fwd(const void* x, void* y, void* idx, long long F, int H, int W, int C, mvfb_stream_t stream);
 int maxpool3x3s2_bwd(const void* g, const void* idx, void* dx, long long F, int H, int W, int C, mvfb_stream_t stream);
 
+/* norm1 + ReLU + maxpool of ResNet.forward (backbones/resnet.py:481-484) in ONE pass over the stem convolution's output, and
+ * the matching backward -- the 112 x 112 x 64 activation and its gradient never exist in memory.
+ *
+ *   bn_relu_maxpool_fwd : x (F, H, W, C) bf16 = conv1 output, `d` as for bn_apply (M = F*H*W, relu = 1; training: mean / var
+ *                         from `sums`, save_mean / save_rstd written, running statistics updated; eval: running statistics)
+ *                         -> y (F, Ho, Wo, C) = maxpool3x3s2(relu(bn(x))) bit for bit, idx (F, Ho, Wo, C) bytes = window
+ *                         position of the winning x (first in scan order), or 9 where the pooled value is <= 0 (the ReLU
+ *                         passes no gradient there).  C / 8 must divide 256.
+ *   bn_relu_maxpool_bwd : g (F, Ho, Wo, C) = dL/dy -> dx (F, H, W, C) = dL/d(conv1 output), dgamma, dbeta (bn_bwd's formulas,
+ *                         g' = the pooled gradients routed to the recorded positions, summed in fp32).  `sums` is [2][C]
+ *                         scratch.  Even H and W.
+ */
+int bn_relu_maxpool_fwd(const mvfb_bn_desc* d, const void* x, long long F, int H, int W, const float* sums, const float* gamma,
+                        const float* beta, float* running_mean, float* running_var, float* save_mean, float* save_rstd, void* y,
+                        void* idx, mvfb_stream_t stream);
+int bn_relu_maxpool_bwd(const mvfb_bn_desc* d, const void* g, const void* idx, const void* x, long long F, int H, int W,
+                        const float* gamma, const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
+                        float* sums, mvfb_stream_t stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Input pre-processing on the GPU  --  replaces Normalize + FormatShape + ToTensor of the data pipeline
  * (codes/datasets/pipelines/augmentations.py:343-396, formating.py:134-185; configs r50_dense.py:70-75) for frames that

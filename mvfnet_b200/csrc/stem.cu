@@ -383,6 +383,271 @@ maxpool_bwd_block_kernel(const uint4* __restrict__ g, const uint2* __restrict__ 
   out[(long long)W * C8 + C8] = pool_pack(acc);
 }
 
+
+// ---------------------------------------------------------------- norm1 + ReLU + max-pool in one pass (and its backward)
+// ResNet.forward's `maxpool(relu(norm1(conv1(x))))` (backbones/resnet.py:481-484).  As three launches the stem's tail
+// moves the largest activation of the network five times (bn_apply: read + write, max-pool: read; backward: the routed
+// gradient written by maxpool_bwd and read twice by bn_bwd).  y = relu(scale * x + shift) rounded to bf16 is a monotone
+// function of x per channel -- non-decreasing for scale >= 0, non-increasing below -- so the window maximum of y is that
+// function of the window's largest (smallest) x: the forward takes the packed-bf16 maximum of the RAW convolution
+// outputs, with the sign bit of the channels whose scale is negative flipped, and applies the affine + ReLU + rounding to
+// the winner only.  The result equals max-pooling the rounded activations bit for bit; the recorded position is the
+// first tap holding the extreme x (where two different x round to the same activation ATen would record the earlier
+// one: both carry the same forward value, and the fp32 reference agrees with THIS choice).  A window whose maximum is
+// <= 0 records position 9, which matches no tap: the ReLU's backward needs nothing else.  The backward gathers the
+// pooled gradient per 2 x 2 input block (maxpool_bwd_block_kernel's scheme) inside BOTH BatchNorm backward passes, so
+// neither the activation nor its gradient ever exists in memory.  Work split as in bn.cu: a thread owns 8 channels.
+struct PoolBnArgs {
+  const uint4* x;                        // (F, H, W, C) convolution output
+  uint4* y;                              // (F, Ho, Wo, C)
+  uint2* idx;                            // (F, Ho, Wo, C) bytes
+  long long F, M;                        // M = F * H * W (the BatchNorm's population)
+  int H, W, Ho, Wo, C8, training;
+  float eps, momentum;
+  const float *sums, *gamma, *beta;
+  float *running_mean, *running_var, *save_mean, *save_rstd;
+};
+
+#ifndef POOLBN_FWD_MINB
+#define POOLBN_FWD_MINB 4
+#endif
+#ifndef POOLBN_RED_MINB
+#define POOLBN_RED_MINB 2
+#endif
+#ifndef POOLBN_APPLY_MINB
+#define POOLBN_APPLY_MINB 2
+#endif
+template <typename I>
+__global__ void __launch_bounds__(256, POOLBN_FWD_MINB)
+bn_relu_maxpool_fwd_kernel(const PoolBnArgs a) {
+  extern __shared__ float4 s_coef[];                             // [2 * C8] scale, then [2 * C8] shift: read once per window
+  const int C8 = a.C8, C = 8 * C8;
+  const int vec = threadIdx.x % C8, rowlane = threadIdx.x / C8, rows_par = 256 / C8;
+  for (int c = threadIdx.x; c < C; c += 256) {                   // bn_apply_kernel's prologue (bn.cu), once per CTA
+    float mean, rstd;
+    if (a.training) {
+      const double m = (double)a.M;
+      const double mu = (double)a.sums[c] / m;
+      double var = (double)a.sums[C + c] / m - mu * mu;
+      if (var < 0) var = 0;
+      mean = (float)mu;
+      rstd = (float)(1.0 / sqrt(var + (double)a.eps));
+      if (blockIdx.x == 0) {
+        a.save_mean[c] = mean;
+        a.save_rstd[c] = rstd;
+        if (a.running_mean) {
+          const double unb = m > 1 ? var * m / (m - 1) : var;
+          a.running_mean[c] = (1.f - a.momentum) * a.running_mean[c] + a.momentum * mean;
+          a.running_var[c] = (1.f - a.momentum) * a.running_var[c] + a.momentum * (float)unb;
+        }
+      }
+    } else {
+      mean = a.running_mean[c];
+      rstd = 1.f / sqrtf(a.running_var[c] + a.eps);
+      if (blockIdx.x == 0 && a.save_mean) { a.save_mean[c] = mean; a.save_rstd[c] = rstd; }
+    }
+    const float sc = a.gamma[c] * rstd;
+    reinterpret_cast<float*>(s_coef)[c] = sc;
+    reinterpret_cast<float*>(s_coef)[C + c] = a.beta[c] - mean * sc;
+  }
+  __syncthreads();
+  uint32_t flip[4];
+  {
+    const float* sc = reinterpret_cast<const float*>(s_coef) + vec * 8;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) flip[q] = (sc[2 * q] < 0.f ? 0x00008000u : 0u) | (sc[2 * q + 1] < 0.f ? 0x80000000u : 0u);
+  }
+  const int H = a.H, W = a.W, Ho = a.Ho, Wo = a.Wo;
+  const int rowp = W * C8;
+  const I npix = (I)(a.F * Ho * Wo);
+  for (I p = (I)blockIdx.x * (I)rows_par + (I)rowlane; p < npix; p += (I)gridDim.x * (I)rows_par) {
+    const int ow = (int)(p % (I)Wo);
+    const I t = p / (I)Wo;
+    const int oh = (int)(t % (I)Ho);
+    const long long f = (long long)(t / (I)Ho);
+    const int ih0 = 2 * oh - 1, iw0 = 2 * ow - 1;
+    const uint4* px = a.x + ((f * H + ih0) * W + iw0) * C8 + vec;
+    uint32_t okmask = 0;
+    uint32_t v[9][4];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int tp = kh * 3 + kw;
+        const bool ok = (unsigned)(ih0 + kh) < (unsigned)H && (unsigned)(iw0 + kw) < (unsigned)W;
+        uint4 q = make_uint4(0xff80ff80u, 0xff80ff80u, 0xff80ff80u, 0xff80ff80u);   // -inf in the flipped domain: never wins
+        if (ok) {
+          q = __ldg(px + kh * rowp + kw * C8);
+          q.x ^= flip[0]; q.y ^= flip[1]; q.z ^= flip[2]; q.w ^= flip[3];
+          okmask |= 1u << tp;
+        }
+        v[tp][0] = q.x; v[tp][1] = q.y; v[tp][2] = q.z; v[tp][3] = q.w;
+      }
+    }
+    uint32_t m[4], a2[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      m[q] = v[0][q];
+#pragma unroll
+      for (int tp = 1; tp < 9; ++tp) m[q] = hmax2_nan(m[q], v[tp][q]);
+      a2[q] = 0x00040004u;
+    }
+#pragma unroll
+    for (int tp = 8; tp >= 0; --tp) {                            // the earliest tap equal to the extreme is written last
+      const uint32_t on = (okmask >> tp) & 1u ? 0xffffffffu : 0u;
+      const uint32_t code = (uint32_t)tp * 0x00010001u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const uint32_t e = heq2(v[tp][q], m[q]) & on;
+        a2[q] = (e & code) | (~e & a2[q]);
+      }
+    }
+    uint32_t o[4];
+    const float4 sc0 = s_coef[2 * vec], sc1 = s_coef[2 * vec + 1], sh0 = s_coef[2 * C8 + 2 * vec], sh1 = s_coef[2 * C8 + 2 * vec + 1];
+    const float scale[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+    const float shift[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const uint32_t raw = m[q] ^ flip[q];
+      const float lo = fmaxf(fmaf(bf16_lo(raw), scale[2 * q], shift[2 * q]), 0.f);
+      const float hi = fmaxf(fmaf(bf16_hi(raw), scale[2 * q + 1], shift[2 * q + 1]), 0.f);
+      o[q] = pack_bf16(lo, hi);
+      if (!(lo > 0.f)) a2[q] = (a2[q] & 0xffff0000u) | 0x00000009u;     // dead ReLU: no tap receives the gradient
+      if (!(hi > 0.f)) a2[q] = (a2[q] & 0x0000ffffu) | 0x00090000u;
+    }
+    const long long oi = (long long)p * C8 + vec;
+    a.y[oi] = make_uint4(o[0], o[1], o[2], o[3]);
+    uint2 k;
+    k.x = __byte_perm(a2[0], a2[1], 0x6420);
+    k.y = __byte_perm(a2[2], a2[3], 0x6420);
+    a.idx[oi] = k;
+  }
+}
+
+struct PoolBnBwdArgs {
+  const uint4* g;                        // (F, Ho, Wo, C) gradient of the pooled output
+  const uint2* idx;
+  const uint4* x;                        // (F, H, W, C) convolution output
+  uint4* dx;                             // (F, H, W, C) gradient of the convolution output
+  long long F, M;
+  int H, W, Ho, Wo, C8, training;
+  const float *gamma, *mean, *rstd;
+  float *sums, *dgamma, *dbeta;          // sums [2][C]: sum g', sum g' xhat
+};
+
+// APPLY = false: sums += (g', g' * xhat) per channel;  APPLY = true: dx = gamma rstd (g' - sum g'/M - xhat sum g' xhat/M).
+// g' of a pixel = the pooled gradients of the <= 4 windows that recorded it (fp32 sum, never rounded to bf16 in between).
+// Per-channel coefficients live in shared memory (three float4 pairs per use) so that the gathers keep the registers:
+//   reduce: xhat = x * k0 + k1                 (k0 = rstd, k1 = -mean rstd)
+//   apply : dx = g' * k0 + (x * k1 + k2)       (k0 = gamma rstd, k1 = -k0 rstd c, k2 = -k0 (b + c k1'),  b = sum g'/M, c = sum g' xhat/M)
+template <bool APPLY, typename I>
+__global__ void __launch_bounds__(256, APPLY ? POOLBN_APPLY_MINB : POOLBN_RED_MINB)
+bn_relu_maxpool_bwd_kernel(const PoolBnBwdArgs a) {
+  extern __shared__ float4 s_dyn[];                              // [3][2 * C8] coefficients, then the reduction scratch
+  const int C8 = a.C8, C = 8 * C8;
+  const int vec = threadIdx.x % C8, rowlane = threadIdx.x / C8, rows_par = 256 / C8;
+  float* s_k = reinterpret_cast<float*>(s_dyn);
+  float* scratch = s_k + 3 * C;
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const float rs = a.rstd[c], mr = -a.mean[c] * rs;
+    if (APPLY) {
+      const float inv_m = 1.f / (float)a.M;
+      const float ga = a.gamma[c] * rs;
+      const float t1 = a.sums[c], t2 = a.sums[C + c];
+      const float b = a.training ? t1 * inv_m : 0.f, cc = a.training ? t2 * inv_m : 0.f;
+      s_k[c] = ga;
+      s_k[C + c] = -ga * cc * rs;
+      s_k[2 * C + c] = -ga * (b + cc * mr);
+      if (blockIdx.x == 0) { a.dbeta[c] = t1; a.dgamma[c] = t2; }
+    } else {
+      s_k[c] = rs;
+      s_k[C + c] = mr;
+    }
+  }
+  __syncthreads();
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) s1[j] = s2[j] = 0.f;
+  const int W = a.W, Ho = a.Ho, Wo = a.Wo;
+  const int rowo = Wo * C8;
+  const long long rowx = (long long)W * C8;
+  const uint4 z4 = make_uint4(0u, 0u, 0u, 0u);
+  const uint2 k9 = make_uint2(0x09090909u, 0x09090909u);
+  const I nblk = (I)(a.F * Ho * Wo);
+  auto use = [&](const float (&gv)[8], const uint4& xq, uint4* out) {
+    const uint32_t xw[4] = {xq.x, xq.y, xq.z, xq.w};
+    const float4 p0 = s_dyn[2 * vec], p1 = s_dyn[2 * vec + 1], q0 = s_dyn[2 * C8 + 2 * vec], q1 = s_dyn[2 * C8 + 2 * vec + 1];
+    const float k0[8] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w};
+    const float k1[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+    float o[8];
+    if (APPLY) {
+      const float4 r0 = s_dyn[4 * C8 + 2 * vec], r1 = s_dyn[4 * C8 + 2 * vec + 1];
+      const float k2[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xv = (j & 1) ? bf16_hi(xw[j >> 1]) : bf16_lo(xw[j >> 1]);
+        o[j] = fmaf(gv[j], k0[j], fmaf(xv, k1[j], k2[j]));
+      }
+      *out = pool_pack(o);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float xv = (j & 1) ? bf16_hi(xw[j >> 1]) : bf16_lo(xw[j >> 1]);
+        s1[j] += gv[j];
+        s2[j] = fmaf(gv[j], fmaf(xv, k0[j], k1[j]), s2[j]);
+      }
+    }
+  };
+  for (I p = (I)blockIdx.x * (I)rows_par + (I)rowlane; p < nblk; p += (I)gridDim.x * (I)rows_par) {
+    const int bb = (int)(p % (I)Wo);
+    const I t = p / (I)Wo;
+    const int aa = (int)(t % (I)Ho);
+    const long long f = (long long)(t / (I)Ho);
+    const bool right = bb + 1 < Wo, down = aa + 1 < Ho;
+    const long long i = (long long)p * C8 + vec;
+    const uint4 g00 = __ldg(a.g + i);
+    const uint2 k00 = __ldg(a.idx + i);
+    const uint4 g01 = right ? __ldg(a.g + i + C8) : z4;
+    const uint2 k01 = right ? __ldg(a.idx + i + C8) : k9;
+    const uint4 g10 = down ? __ldg(a.g + i + rowo) : z4;
+    const uint2 k10 = down ? __ldg(a.idx + i + rowo) : k9;
+    const uint4 g11 = (right && down) ? __ldg(a.g + i + rowo + C8) : z4;
+    const uint2 k11 = (right && down) ? __ldg(a.idx + i + rowo + C8) : k9;
+    const long long xo = ((f * (2 * Ho) + 2 * aa) * (long long)W + 2 * bb) * C8 + vec;
+    const uint4 x00 = __ldg(a.x + xo), x01 = __ldg(a.x + xo + C8), x10 = __ldg(a.x + xo + rowx), x11 = __ldg(a.x + xo + rowx + C8);
+    uint4* out = a.dx + xo;
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    pool_take(acc, g00, k00, 4u);
+    use(acc, x00, out);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    pool_take(acc, g00, k00, 5u); pool_take(acc, g01, k01, 3u);
+    use(acc, x01, out + C8);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    pool_take(acc, g00, k00, 7u); pool_take(acc, g10, k10, 1u);
+    use(acc, x10, out + rowx);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    pool_take(acc, g00, k00, 8u); pool_take(acc, g01, k01, 6u); pool_take(acc, g10, k10, 2u); pool_take(acc, g11, k11, 0u);
+    use(acc, x11, out + rowx + C8);
+  }
+  if (!APPLY) {                                                  // registers -> shared memory -> one atomic per channel and CTA
+    float* mine = scratch + (size_t)threadIdx.x * 16;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { mine[j] = s1[j]; mine[8 + j] = s2[j]; }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C8 * 16; i += 256) {
+      const int v = i / 16, q = i - v * 16;
+      float s = 0.f;
+      for (int r = 0; r < rows_par; ++r) s += scratch[(size_t)(r * C8 + v) * 16 + q];
+      atomicAdd(&a.sums[(q >> 3) * C + v * 8 + (q & 7)], s);
+    }
+  }
+}
+
 }  // namespace
 
 }  // namespace mvfb
@@ -458,6 +723,72 @@ int maxpool3x3s2_bwd(const void* g, const void* idx, void* dx, long long F, int 
   else
     maxpool_bwd_kernel<long long><<<(unsigned)ceil_div_ll(total, 256), 256, 0, (cudaStream_t)stream>>>(
         (const uint4*)g, (const uint2*)idx, (uint4*)dx, H, W, Ho, Wo, C / 8, total);
+  count_launch();
+  MVFB_LAUNCH_CHECK();
+  return MVFB_OK;
+}
+
+int bn_relu_maxpool_fwd(const mvfb_bn_desc* d, const void* x, long long F, int H, int W, const float* sums, const float* gamma,
+                        const float* beta, float* running_mean, float* running_var, float* save_mean, float* save_rstd, void* y,
+                        void* idx, mvfb_stream_t stream) {
+  MVFB_CHECK(d && x && y && idx && gamma && beta && F > 0 && H > 0 && W > 0, MVFB_ERR_ARG, "bn_relu_maxpool_fwd: bad arguments");
+  MVFB_CHECK(d->C > 0 && d->C % 8 == 0 && 256 % (d->C / 8) == 0 && d->relu && d->M == F * H * W, MVFB_ERR_UNSUPPORTED,
+             "bn_relu_maxpool_fwd: C / 8 must divide 256, relu = 1, M = F*H*W");
+  MVFB_CHECK(d->training ? (sums && save_mean && save_rstd) : (running_mean && running_var), MVFB_ERR_ARG,
+             "bn_relu_maxpool_fwd: training needs sums / save_*, inference the running statistics");
+  MVFB_CHECK(!((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) && !(reinterpret_cast<uintptr_t>(idx) & 7),
+             MVFB_ERR_ARG, "bn_relu_maxpool_fwd: misaligned tensors");
+  PoolBnArgs a;
+  a.x = (const uint4*)x; a.y = (uint4*)y; a.idx = (uint2*)idx;
+  a.F = F; a.M = d->M; a.H = H; a.W = W; a.Ho = (H - 1) / 2 + 1; a.Wo = (W - 1) / 2 + 1; a.C8 = d->C / 8;
+  a.training = d->training; a.eps = d->eps; a.momentum = d->momentum;
+  a.sums = sums; a.gamma = gamma; a.beta = beta;
+  a.running_mean = running_mean; a.running_var = running_var; a.save_mean = save_mean; a.save_rstd = save_rstd;
+  const long long npix = F * a.Ho * a.Wo;
+  const int rows_par = 256 / a.C8;
+  long long blocks = ceil_div_ll(npix, rows_par);
+  if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+  if (npix < (1LL << 31) - (1LL << 24))
+    bn_relu_maxpool_fwd_kernel<uint32_t><<<(unsigned)blocks, 256, 2 * d->C * sizeof(float), (cudaStream_t)stream>>>(a);
+  else
+    bn_relu_maxpool_fwd_kernel<long long><<<(unsigned)blocks, 256, 2 * d->C * sizeof(float), (cudaStream_t)stream>>>(a);
+  count_launch();
+  MVFB_LAUNCH_CHECK();
+  return MVFB_OK;
+}
+
+int bn_relu_maxpool_bwd(const mvfb_bn_desc* d, const void* g, const void* idx, const void* x, long long F, int H, int W,
+                        const float* gamma, const float* mean, const float* rstd, void* dx, float* dgamma, float* dbeta,
+                        float* sums, mvfb_stream_t stream) {
+  MVFB_CHECK(d && g && idx && x && dx && gamma && mean && rstd && dgamma && dbeta && sums && F > 0 && H > 0 && W > 0, MVFB_ERR_ARG,
+             "bn_relu_maxpool_bwd: bad arguments");
+  MVFB_CHECK(d->C > 0 && d->C % 8 == 0 && 256 % (d->C / 8) == 0 && d->relu && d->M == F * H * W && H % 2 == 0 && W % 2 == 0,
+             MVFB_ERR_UNSUPPORTED, "bn_relu_maxpool_bwd: C / 8 must divide 256, relu = 1, M = F*H*W, even H and W");
+  MVFB_CHECK(!((reinterpret_cast<uintptr_t>(g) | reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dx)) & 15) &&
+                 !(reinterpret_cast<uintptr_t>(idx) & 7),
+             MVFB_ERR_ARG, "bn_relu_maxpool_bwd: misaligned tensors");
+  cudaStream_t st = (cudaStream_t)stream;
+  PoolBnBwdArgs a;
+  a.g = (const uint4*)g; a.idx = (const uint2*)idx; a.x = (const uint4*)x; a.dx = (uint4*)dx;
+  a.F = F; a.M = d->M; a.H = H; a.W = W; a.Ho = H / 2; a.Wo = W / 2; a.C8 = d->C / 8; a.training = d->training;
+  a.gamma = gamma; a.mean = mean; a.rstd = rstd; a.sums = sums; a.dgamma = dgamma; a.dbeta = dbeta;
+  MVFB_CUDA(cudaMemsetAsync(sums, 0, sizeof(float) * 2 * d->C, st));
+  const long long nblk = F * a.Ho * a.Wo;
+  const int rows_par = 256 / a.C8;
+  long long blocks = ceil_div_ll(nblk, rows_par);
+  if (blocks > (long long)num_sms() * 16) blocks = (long long)num_sms() * 16;
+  const size_t coef = 3 * (size_t)d->C * sizeof(float), red = coef + 256 * 16 * sizeof(float);   // C <= 2048: <= 40 KB
+  if (nblk < (1LL << 31) - (1LL << 24)) {
+    bn_relu_maxpool_bwd_kernel<false, uint32_t><<<(unsigned)blocks, 256, red, st>>>(a);
+    count_launch();
+    MVFB_LAUNCH_CHECK();
+    bn_relu_maxpool_bwd_kernel<true, uint32_t><<<(unsigned)blocks, 256, coef, st>>>(a);
+  } else {
+    bn_relu_maxpool_bwd_kernel<false, long long><<<(unsigned)blocks, 256, red, st>>>(a);
+    count_launch();
+    MVFB_LAUNCH_CHECK();
+    bn_relu_maxpool_bwd_kernel<true, long long><<<(unsigned)blocks, 256, coef, st>>>(a);
+  }
   count_launch();
   MVFB_LAUNCH_CHECK();
   return MVFB_OK;

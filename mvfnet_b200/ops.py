@@ -81,6 +81,10 @@ def _L():
         L.maxpool3x3s2_fwd.argtypes = [_VP, _VP, _VP, _LL, C.c_int, C.c_int, C.c_int, _VP]
         L.maxpool3x3s2_bwd.restype = C.c_int
         L.maxpool3x3s2_bwd.argtypes = [_VP, _VP, _VP, _LL, C.c_int, C.c_int, C.c_int, _VP]
+        L.bn_relu_maxpool_fwd.restype = C.c_int
+        L.bn_relu_maxpool_fwd.argtypes = [C.POINTER(BnDesc), _VP, _LL, C.c_int, C.c_int] + [_VP] * 10
+        L.bn_relu_maxpool_bwd.restype = C.c_int
+        L.bn_relu_maxpool_bwd.argtypes = [C.POINTER(BnDesc), _VP, _VP, _VP, _LL, C.c_int, C.c_int] + [_VP] * 8
         _declared = True
     return L
 
@@ -969,6 +973,85 @@ class _BNAct(torch.autograd.Function):
         _lib.check(rc, "bn_bwd")
         dres_v = dres.permute(0, 3, 1, 2) if dres is not None else None
         return dx.permute(0, 3, 1, 2), grads[0], grads[1], None, None, dres_v, None, None, None, None, None
+
+
+def stem_fuse_enabled() -> bool:
+    """MVFB_STEM_FUSE=0 keeps norm1 / ReLU / max-pool of the stem as separate launches (A/B measurements only)."""
+    return os.environ.get("MVFB_STEM_FUSE", "1") != "0"
+
+
+def bn_relu_maxpool_eligible(x, bn, pool) -> bool:
+    """norm1 + ReLU + maxpool in one pass: bn_act's and maxpool3x3s2's conditions, even H and W, C / 8 dividing 256."""
+    return (stem_fuse_enabled() and bn_eligible(x, bn) and maxpool_eligible(x, pool) and x.shape[2] % 2 == 0
+            and x.shape[3] % 2 == 0 and 256 % (x.shape[1] // 8) == 0)
+
+
+class _BNReluMaxPool(torch.autograd.Function):
+    """maxpool3x3s2(relu(BatchNorm2d(x))) on a bf16 channels_last tensor without materialising the activation
+    (bn_relu_maxpool_fwd / _bwd, include/mvf_b200.h; backbones/resnet.py:481-484)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, sums, training, eps, momentum):
+        L = _L()
+        f, c, h, w = x.shape
+        d = BnDesc()
+        d.M, d.C, d.relu, d.training, d.eps, d.momentum = f * h * w, c, 1, int(training), eps, momentum
+        dev = x.device
+        xr = _rows(x)
+        if training and sums is None:
+            sums = torch.empty((2, c), dtype=torch.float32, device=dev)
+            with _T("bn_fwd", nbytes=2 * xr.numel()):
+                _lib.check(L.bn_stats(C.byref(d), ptr(xr), xr.stride(0), ptr(sums), _stream()), "bn_stats")
+        ho, wo = h // 2, w // 2
+        y = torch.empty((f, ho, wo, c), dtype=torch.bfloat16, device=dev)
+        idx = torch.empty((f, ho, wo, c), dtype=torch.uint8, device=dev)
+        save = torch.empty((2, c), dtype=torch.float32, device=dev)
+        g32 = gamma if gamma.dtype == torch.float32 else gamma.float()
+        b32 = beta if beta.dtype == torch.float32 else beta.float()
+        with _T("bn_fwd", nbytes=2 * xr.numel() + 3 * y.numel()):
+            rc = L.bn_relu_maxpool_fwd(C.byref(d), ptr(xr), f, h, w, ptr(sums), ptr(g32), ptr(b32), ptr(running_mean),
+                                       ptr(running_var), ptr(save[0]), ptr(save[1]), ptr(y), ptr(idx), _stream())
+        _lib.check(rc, "bn_relu_maxpool_fwd")
+        ctx.training, ctx.eps = training, eps
+        ctx.save_for_backward(x, idx, g32, save)
+        return y.permute(0, 3, 1, 2)
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _L()
+        x, idx, gamma, save = ctx.saved_tensors
+        f, c, h, w = x.shape
+        g = g.to(torch.bfloat16).contiguous(memory_format=torch.channels_last)
+        d = BnDesc()
+        d.M, d.C, d.relu, d.training, d.eps, d.momentum = f * h * w, c, 1, int(ctx.training), ctx.eps, 0.0
+        dev = x.device
+        dx = torch.empty((f, h, w, c), dtype=torch.bfloat16, device=dev)
+        grads = torch.empty((2, c), dtype=torch.float32, device=dev)
+        scratch = torch.empty((2, c), dtype=torch.float32, device=dev)
+        ne, npool = x.numel(), idx.numel()
+        # both passes read the pooled gradient, the positions and the convolution output; the second writes dx
+        with _T("bn_bwd", nbytes=2 * (3 * npool + 2 * ne) + 2 * ne):
+            rc = L.bn_relu_maxpool_bwd(C.byref(d), ptr(g), ptr(idx), ptr(_rows(x)), f, h, w, ptr(gamma), ptr(save[0]),
+                                       ptr(save[1]), ptr(dx), ptr(grads[0]), ptr(grads[1]), ptr(scratch), _stream())
+        _lib.check(rc, "bn_relu_maxpool_bwd")
+        return dx.permute(0, 3, 1, 2), grads[0], grads[1], None, None, None, None, None, None
+
+
+def bn_relu_maxpool(x, bn, sums=None):
+    """`pool(relu(bn(x)))` for nn.MaxPool2d(3, 2, 1); `bn` owns the parameters and running statistics (bn_act's contract)."""
+    training = bool(bn.training or not bn.track_running_stats)
+    rm = rv = None
+    momentum = 0.0
+    if bn.track_running_stats:
+        rm, rv = bn.running_mean, bn.running_var
+        if training:
+            momentum = 1.0 / float(int(bn.num_batches_tracked) + 1) if bn.momentum is None else float(bn.momentum)
+    if not training:
+        sums = None
+    y = _BNReluMaxPool.apply(x, bn.weight, bn.bias, rm, rv, sums, training, float(bn.eps), momentum)
+    if training and bn.track_running_stats:
+        count_batch(bn)
+    return y
 
 
 def bn_act(x, bn, relu=True, residual=None, sums=None):

@@ -264,6 +264,8 @@ class ResNet(nn.Module):
             out, sums = ops.stem_conv(x, self.conv1.weight, True)
         else:
             out, sums = self.conv1(x), None
+        if ops.bn_relu_maxpool_eligible(out, self.norm1, self.maxpool):   # one pass, the activation is never stored
+            return ops.bn_relu_maxpool(out, self.norm1, sums=sums)
         out = _bn_act(self.norm1, out, True, sums=sums, relu_module=self.relu)
         if ops.maxpool_eligible(out, self.maxpool):
             return ops.maxpool3x3s2(out)

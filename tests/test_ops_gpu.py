@@ -15,6 +15,11 @@ def rel(a, b):
     return float((a - b).abs().max() / b.abs().max().clamp_min(1e-12))
 
 
+def _lib_launches():
+    from mvfnet_b200 import _lib
+    return _lib.launch_count()
+
+
 def rel_l2(a, b):
     """||a - b|| / ||b||: for gradients that passed through ReLU masks.  A bf16 and an fp32 pipeline legitimately
     disagree on the mask of the few activations whose pre-activation is within rounding distance of 0, and each flip
@@ -288,6 +293,57 @@ def test_maxpool3x3s2_vs_torch(F, C, H, W):
     ya.backward(gy)
     yb.backward(gy)
     assert torch.equal(xa.grad, xb.grad)
+
+
+@pytest.mark.parametrize("F,C,H,W,training", [(4, 64, 112, 112, True), (3, 64, 16, 20, True), (2, 32, 8, 8, True),
+                                               (5, 128, 14, 14, True), (3, 64, 16, 20, False)])
+def test_bn_relu_maxpool_fused_vs_separate_and_torch(F, C, H, W, training):
+    """norm1 + ReLU + maxpool in one pass (bn_relu_maxpool_fwd / _bwd): the pooled output equals the three-launch path
+    (bn_apply, then maxpool3x3s2 of the rounded activation) BIT FOR BIT, channels with a negative gamma included (the
+    maximum of a decreasing function is taken at the window's minimum); running statistics equal to rounding; input / gamma / beta
+    gradients match both the separate launches and torch's fp32 BatchNorm2d -> ReLU -> MaxPool2d on the same bf16 input."""
+    from mvfnet_b200 import ops
+    g = torch.Generator().manual_seed(F * 1000 + C + H)
+    x = (torch.randn((F, C, H, W), generator=g) * 1.5 + 0.3).cuda().bfloat16().contiguous(memory_format=torch.channels_last)
+    gamma = torch.randn(C, generator=g) * 0.8 + 0.5            # a good share negative
+    assert (gamma < 0).any() and (gamma > 0).any()
+    beta = torch.randn(C, generator=g) * 0.3
+    pool = torch.nn.MaxPool2d(3, 2, 1)
+
+    def make_bn():
+        bn = torch.nn.BatchNorm2d(C).cuda()
+        with torch.no_grad():
+            bn.weight.copy_(gamma); bn.bias.copy_(beta)
+            bn.running_mean.copy_(torch.linspace(-0.2, 0.4, C)); bn.running_var.copy_(torch.linspace(0.5, 2.0, C))
+        bn.train(training)
+        return bn
+    bn_a, bn_b, bn_c = make_bn(), make_bn(), make_bn()
+    assert ops.bn_relu_maxpool_eligible(x, bn_a, pool)
+    xa, xb, xc = (x.clone().requires_grad_(True) for _ in range(3))
+    # the same statistics for both paths (bn_stats adds its partial sums with atomics: two runs differ in the last bit)
+    sums = torch.stack([x.float().sum((0, 2, 3)), (x.float() ** 2).sum((0, 2, 3))]).contiguous() if training else None
+    launches = _lib_launches()
+    ya = ops.bn_relu_maxpool(xa, bn_a, sums=sums)
+    assert _lib_launches() - launches == 1
+    yb = ops.maxpool3x3s2(ops.bn_act(xb, bn_b, relu=True, sums=sums))
+    yc = pool(torch.relu(bn_c(xc.float())))
+    assert torch.equal(ya, yb)
+    assert rel(ya, yc) < 6e-3
+    assert rel(bn_a.running_mean, bn_b.running_mean) < 1e-6 and rel(bn_a.running_var, bn_b.running_var) < 1e-6
+    assert rel(bn_a.running_var, bn_c.running_var) < 1e-4
+    gy = torch.randn(yc.shape, generator=g).cuda().bfloat16().contiguous(memory_format=torch.channels_last)
+    ya.backward(gy); yb.backward(gy); yc.backward(gy.float())
+    print("dgamma vs fp32 %.2e, vs separate %.2e; dbeta vs fp32 %.2e, vs separate %.2e; dx vs fp32 %.2e (separate launches: %.2e)" % (
+        rel(bn_a.weight.grad, bn_c.weight.grad), rel(bn_a.weight.grad, bn_b.weight.grad), rel(bn_a.bias.grad, bn_c.bias.grad), rel(bn_a.bias.grad, bn_b.bias.grad), rel_l2(xa.grad, xc.grad), rel_l2(xb.grad, xc.grad)))
+    # The fused pass reproduces the fp32 reference's gradients to rounding.  The separate launches do not: where a window's
+    # largest inputs are different bf16 numbers whose activations round to the SAME bf16 number (frequent for a small
+    # |gamma|), max-pooling the rounded activation sends the gradient to the earliest of them -- as ATen's bf16 pipeline
+    # does -- while the fused pass and the fp32 reference send it to the largest input: 2-3 % of dx's energy, up to 9 %
+    # of a dgamma entry at 112 x 112.
+    assert rel_l2(xa.grad, xc.grad) < 1e-3 and rel_l2(xa.grad, xb.grad) < 5e-2
+    assert rel(bn_a.weight.grad, bn_c.weight.grad) < 1e-4 and rel(bn_a.bias.grad, bn_c.bias.grad) < 1e-4
+    assert rel(bn_a.weight.grad, bn_b.weight.grad) < 0.15 and rel(bn_a.bias.grad, bn_b.bias.grad) < 1e-2
+    assert rel_l2(xa.grad, xc.grad) <= rel_l2(xb.grad, xc.grad) + 1e-6
 
 
 def test_maxpool3x3s2_negative_values_and_nans():
