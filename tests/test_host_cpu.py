@@ -66,6 +66,31 @@ def test_stem_and_workspace_host_logic_without_gpu():
         assert nbytes <= 148 * 2 * 64 * 8 + 16 * 8 * Cs + 4096       # never more than one 64-channel row per SM (+ generic)
 
 
+def test_fused_stem_tail_argument_errors_without_gpu():
+    """bn_relu_maxpool_fwd / _bwd (norm1 + ReLU + max-pool in one pass) reject bad calls before any CUDA call: null
+    tensors, a population that is not F*H*W, a channel count whose 8-channel vectors do not divide the 256-thread CTA,
+    a backward over odd sizes (its 2 x 2 input blocks need even H and W)."""
+    from mvfnet_b200 import ops
+    L = ops._L()
+    d = ops.BnDesc()
+    d.M, d.C, d.relu, d.training, d.eps, d.momentum = 4 * 112 * 112, 64, 1, 1, 1e-5, 0.1
+    nul = [None] * 10
+    assert L.bn_relu_maxpool_fwd(ctypes.byref(d), None, 4, 112, 112, *nul) == 1 and b"bn_relu_maxpool_fwd" in L.mvf_b200_last_error()
+    buf = (ctypes.c_char * 4096)()
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    ten = [p] * 10
+    d.M = 5 * 112 * 112                                                  # M != F*H*W
+    assert L.bn_relu_maxpool_fwd(ctypes.byref(d), p, 4, 112, 112, *ten) == 3 and b"M = F*H*W" in L.mvf_b200_last_error()
+    d.M, d.C = 4 * 112 * 112, 24                                         # 3 vectors per pixel do not divide 256
+    assert L.bn_relu_maxpool_fwd(ctypes.byref(d), p, 4, 112, 112, *ten) == 3
+    d.C, d.relu = 64, 0                                                  # the fusion IS the ReLU
+    assert L.bn_relu_maxpool_fwd(ctypes.byref(d), p, 4, 112, 112, *ten) == 3
+    d.relu, d.M = 1, 4 * 111 * 112
+    eight = [p] * 8
+    assert L.bn_relu_maxpool_bwd(ctypes.byref(d), p, p, p, 4, 111, 112, *eight) == 3 and b"even H and W" in L.mvf_b200_last_error()
+    assert L.bn_relu_maxpool_bwd(ctypes.byref(d), None, p, p, 4, 112, 112, *eight) == 1
+
+
 def test_registry_contract():
     from mvfnet_b200 import Registry, build_from_cfg, RECOGNIZERS, BACKBONES, HEADS
     assert "Recognizer2D" in RECOGNIZERS.module_dict and "ResNet" in BACKBONES.module_dict and "TSNClsHead" in HEADS.module_dict
