@@ -1,7 +1,10 @@
 #!/bin/bash
-# compute-sanitizer over the last kernels of the round: fused norm1 + ReLU + max-pool, CTA pairs in the halo convolution
+# compute-sanitizer over the last kernels of the round: fused norm1 + ReLU + max-pool, CTA pairs in the halo convolution.
+# A tensor-map (driver API) kernel runs first: when the process's very first library launch is a plain <<<>>> launch, memcheck
+# reports one CUDA_ERROR_INVALID_HANDLE from cudart's internal cuKernelGetFunction probe (lazy module loading; the launch
+# itself succeeds and the test passes).
 set -u
 cd "$(dirname "$0")/../.."
 mkdir -p gpurun_out
-echo "== memcheck"; timeout 100 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_ops_gpu.py -m gpu -q -x -k "(bn_relu_maxpool and not 112) or conv_halo_cta_pair" > gpurun_out/san3_memcheck.log 2>&1; echo "rc=$?" >> gpurun_out/san3_memcheck.log; tail -4 gpurun_out/san3_memcheck.log | cut -c1-200
+echo "== memcheck"; timeout 100 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_ops_gpu.py -m gpu -q -x -k "(gemm_tn_matches and 128-64-64) or (bn_relu_maxpool and not 112) or conv_halo_cta_pair" > gpurun_out/san3_memcheck.log 2>&1; echo "rc=$?" >> gpurun_out/san3_memcheck.log; tail -4 gpurun_out/san3_memcheck.log | cut -c1-200
 echo "== racecheck"; timeout 70 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_ops_gpu.py -m gpu -q -x -k "(bn_relu_maxpool and 8-8) or (conv_halo_cta_pair and 50-64)" > gpurun_out/san3_racecheck.log 2>&1; echo "rc=$?" >> gpurun_out/san3_racecheck.log; tail -4 gpurun_out/san3_racecheck.log | cut -c1-200
